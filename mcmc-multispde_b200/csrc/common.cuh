@@ -1,0 +1,80 @@
+// Shared declarations for libmspde (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+typedef double2 cplx;   // complex128, interleaved (re, im) -- same bits as numpy/torch complex128
+
+namespace mspde {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define MSPDE_CUDA(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            mspde::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,             \
+                             cudaGetErrorString(e__));                                        \
+            return -1;                                                                        \
+        }                                                                                     \
+    } while (0)
+
+#define MSPDE_LAUNCH_CHECK()                                                                  \
+    do {                                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess) {                                                             \
+            mspde::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,         \
+                             cudaGetErrorString(e__));                                        \
+            return -1;                                                                        \
+        }                                                                                     \
+    } while (0)
+
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b) {   // conj(a) * b
+    return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx c) {   // a*b + c
+    c.x = fma(a.x, b.x, c.x); c.x = fma(-a.y, b.y, c.x);
+    c.y = fma(a.x, b.y, c.y); c.y = fma(a.y, b.x, c.y);
+    return c;
+}
+__device__ __forceinline__ cplx cfmac(cplx a, cplx b, cplx c) {  // conj(a)*b + c
+    c.x = fma(a.x, b.x, c.x); c.x = fma(a.y, b.y, c.x);
+    c.y = fma(a.x, b.y, c.y); c.y = fma(-a.y, b.x, c.y);
+    return c;
+}
+__device__ __forceinline__ cplx cfnma(cplx a, cplx b, cplx c) {  // c - a*b
+    c.x = fma(-a.x, b.x, c.x); c.x = fma(a.y, b.y, c.x);
+    c.y = fma(-a.x, b.y, c.y); c.y = fma(-a.y, b.x, c.y);
+    return c;
+}
+__device__ __forceinline__ cplx cfnmac(cplx a, cplx b, cplx c) { // c - conj(a)*b
+    c.x = fma(-a.x, b.x, c.x); c.x = fma(-a.y, b.y, c.x);
+    c.y = fma(-a.x, b.y, c.y); c.y = fma(a.y, b.x, c.y);
+    return c;
+}
+__device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+// Smith-free complex division; operands are O(1)-scaled in every caller.
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+    double d = b.x * b.x + b.y * b.y;
+    return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+
+// ---- GEMM (zgemm_tn.cu) --------------------------------------------------------------------------
+enum { GEMM_FULL = 0, GEMM_UPPER = 1 };
+// C[i][j] = alpha * sum_k opA(A[k][i]) * B[k][j] + beta * C[i][j];  A: k x m, B: k x n, C: m x n, row-major.
+int zgemm_tn(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, const cplx* A, int lda,
+             const cplx* B, int ldb, double beta, cplx* C, int ldc, int uplo);
+// Split-K variant: partial products into `part` (nsplit slices of m x n, ld n), then a deterministic reduce.
+int zgemm_tn_splitk(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, const cplx* A, int lda,
+                    const cplx* B, int ldb, double beta, cplx* C, int ldc, cplx* part, int nsplit);
+
+}  // namespace mspde

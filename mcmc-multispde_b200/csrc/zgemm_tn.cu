@@ -1,0 +1,295 @@
+// Complex FP64 GEMM on the FP64 tensor pipe (DMMA m8n8k4) for sm_100a.
+//
+//   C[i][j] = alpha * sum_k opA(A[k][i]) * B[k][j] + beta * C[i][j]       opA = identity | conj
+//
+// A is K x m, B is K x n, C is m x n, all row-major interleaved complex128.  This single "TN" form is
+// what every dense step of the pCN path reduces to (L^H L, U12^H U12 trailing updates, U^-H B solves,
+// V^H A block reflectors): both operands are read along contiguous rows, so tiles are fetched with
+// 1-D TMA bulk copies (cp.async.bulk.shared::cluster.global, one row segment per copy, mbarrier
+// complete_tx) into padded, bank-conflict-free shared-memory rows.
+//
+// Complex arithmetic stays 4M (no Gauss/3M trick): a complex m x n x k product is run as the real
+// product  C(m x 2n) = A(m x 2k) * B~(2k x 2n)  where A is used as stored (interleaved re/im along k)
+// and B~ is the real 2x2 expansion [[br, bi], [-bi, br]] of B.  The expansion is never materialised: a
+// lane of the k4 x n8 "col" fragment picks its component ((k'&1)^(n'&1)) and sign ((k'&1)&!(n'&1)) when
+// it loads from shared memory.  One DMMA.8x8x4 therefore performs a complex 8 x 4 x 2 product with no
+// wasted flops, and the accumulator fragment (row g, cols 2t,2t+1) is exactly one complex C element.
+#include "common.cuh"
+
+namespace mspde {
+
+namespace {
+
+constexpr int BM = 64;          // C tile rows (i)
+constexpr int BN = 64;          // C tile cols (j), complex
+constexpr int BK = 16;          // complex k per stage
+constexpr int STAGES = 3;
+constexpr int PA = BM + 4;      // smem row pitch (complex); == 4 mod 8 -> conflict-free fragment loads
+constexpr int PB = BN + 4;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int STAGE_DOUBLES = (BK * PA + BK * PB) * 2;
+constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double flip(double x, int signmask) {
+    return __hiloint2double(__double2hiint(x) ^ signmask, __double2loint(x));
+}
+
+struct GemmArgs {
+    const cplx* A;
+    const cplx* B;
+    cplx* C;
+    int m, n, k;
+    int lda, ldb, ldc;
+    double alpha, beta;
+    int conjA;
+    int uplo;
+    int kslice;             // k per blockIdx.z slice
+    long long cslice;       // C stride (complex elements) per slice
+};
+
+__global__ void __launch_bounds__(THREADS, 2) zgemm_tn_kernel(GemmArgs p) {
+    const int i0 = blockIdx.x * BM;
+    const int j0 = blockIdx.y * BN;
+    if (p.uplo == GEMM_UPPER && j0 + BN - 1 < i0) return;   // tile entirely below the diagonal
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage_base = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + size_t(STAGES) * STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty_bar = full_bar + STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    const int kbeg = blockIdx.z * p.kslice;
+    const int kend = min(p.k, kbeg + p.kslice);
+    const int klen = kend - kbeg;
+    const int ktiles = (klen + BK - 1) / BK;
+    cplx* __restrict__ C = p.C + size_t(blockIdx.z) * p.cslice;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int mrows = min(BM, p.m - i0);   // valid A columns (= C rows) in this tile
+    const int ncols = min(BN, p.n - j0);
+
+    if (warp == CONSUMER_WARPS) {
+        // ---------------- producer warp: lanes 0-15 fetch A rows, lanes 16-31 fetch B rows ----------------
+        const bool isA = lane < BK;
+        const int r = isA ? lane : lane - BK;
+        const cplx* src_base = isA ? (p.A + size_t(kbeg) * p.lda + i0) : (p.B + size_t(kbeg) * p.ldb + j0);
+        const size_t ld = isA ? p.lda : p.ldb;
+        const uint32_t row_bytes = uint32_t(isA ? mrows : ncols) * 16u;
+        const int dst_off = isA ? r * PA * 2 : (BK * PA + r * PB) * 2;
+        int stage = 0;
+        uint32_t parity = 0;
+        for (int kt = 0; kt < ktiles; ++kt) {
+            mbar_wait(&empty_bar[stage], parity ^ 1);
+            const int kvalid = min(BK, klen - kt * BK);
+            if (lane == 0) mbar_expect_tx(&full_bar[stage], uint32_t(kvalid) * uint32_t(mrows + ncols) * 16u);
+            __syncwarp();
+            if (r < kvalid) {
+                bulk_g2s(stage_base + size_t(stage) * STAGE_DOUBLES + dst_off, src_base + (size_t(kt) * BK + r) * ld,
+                         row_bytes, &full_bar[stage]);
+            }
+            if (++stage == STAGES) { stage = 0; parity ^= 1; }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int wi = warp & 1;          // 2 warps along i (32 rows each)
+    const int wj = warp >> 1;         // 4 warps along j (16 complex cols each)
+    const int a_sign = (p.conjA && (t & 1)) ? 0x80000000 : 0;
+    const int b_sign = ((t & 1) && !(g & 1)) ? 0x80000000 : 0;
+    const int a_off = ((t >> 1) * PA + wi * 32 + g) * 2 + (t & 1);
+    const int b_off = (BK * PA + (t >> 1) * PB + wj * 16 + (g >> 1)) * 2 + ((t & 1) ^ (g & 1));
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int kt = 0; kt < ktiles; ++kt) {
+        mbar_wait(&full_bar[stage], parity);
+        const double* S = stage_base + size_t(stage) * STAGE_DOUBLES;
+        const int kvalid = klen - kt * BK;
+        if (kvalid >= BK) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 2; ++kk) {
+                double af[4], bf[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) af[a] = flip(S[a_off + kk * 2 * PA * 2 + a * 16], a_sign);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) bf[b] = flip(S[b_off + kk * 2 * PB * 2 + b * 8], b_sign);
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
+        } else {
+            // k tail: rows >= kvalid of the stage were not fetched; feed zeros for them
+            const int nk4 = (kvalid + 1) >> 1;
+            for (int kk = 0; kk < nk4; ++kk) {
+                const bool dead = (kk * 2 + (t >> 1)) >= kvalid;
+                double af[4], bf[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) af[a] = dead ? 0.0 : flip(S[a_off + kk * 2 * PA * 2 + a * 16], a_sign);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) bf[b] = dead ? 0.0 : flip(S[b_off + kk * 2 * PB * 2 + b * 8], b_sign);
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; parity ^= 1; }
+    }
+
+    // ---------------- epilogue: one complex element per lane per fragment ----------------
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + wi * 32 + a * 8 + g;
+        if (i >= p.m) continue;
+        cplx* crow = C + size_t(i) * p.ldc;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = j0 + wj * 16 + b * 4 + t;
+            if (j >= p.n) continue;
+            if (p.uplo == GEMM_UPPER && j < i) continue;
+            cplx out = make_double2(alpha * acc[a][b][0], alpha * acc[a][b][1]);
+            if (beta != 0.0) {
+                cplx c = crow[j];
+                out.x = fma(beta, c.x, out.x);
+                out.y = fma(beta, c.y, out.y);
+            }
+            crow[j] = out;
+        }
+    }
+}
+
+__global__ void splitk_reduce_kernel(const cplx* __restrict__ part, int nsplit, long long slice, int m, int n,
+                                     double alpha, double beta, cplx* __restrict__ C, int ldc) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)m * n) return;
+    int i = int(idx / n), j = int(idx % n);
+    double sx = 0.0, sy = 0.0;
+    for (int s = 0; s < nsplit; ++s) {
+        cplx v = part[s * slice + idx];
+        sx += v.x;
+        sy += v.y;
+    }
+    cplx* c = C + size_t(i) * ldc + j;
+    cplx out = make_double2(alpha * sx, alpha * sy);
+    if (beta != 0.0) {
+        cplx old = *c;
+        out.x = fma(beta, old.x, out.x);
+        out.y = fma(beta, old.y, out.y);
+    }
+    *c = out;
+}
+
+bool g_attr_set = false;
+
+int launch(cudaStream_t st, const GemmArgs& a, int nz) {
+    if (a.m <= 0 || a.n <= 0) return 0;
+    if (!g_attr_set) {
+        MSPDE_CUDA(cudaFuncSetAttribute(zgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        g_attr_set = true;
+    }
+    dim3 grid((a.m + BM - 1) / BM, (a.n + BN - 1) / BN, nz);
+    zgemm_tn_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    MSPDE_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+int zgemm_tn(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, const cplx* A, int lda, const cplx* B,
+             int ldb, double beta, cplx* C, int ldc, int uplo) {
+    GemmArgs a;
+    a.A = A; a.B = B; a.C = C;
+    a.m = m; a.n = n; a.k = k;
+    a.lda = lda; a.ldb = ldb; a.ldc = ldc;
+    a.alpha = alpha; a.beta = beta;
+    a.conjA = conjA ? 1 : 0;
+    a.uplo = uplo;
+    a.kslice = k > 0 ? k : 1;
+    a.cslice = 0;
+    return launch(st, a, 1);
+}
+
+int zgemm_tn_splitk(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, const cplx* A, int lda,
+                    const cplx* B, int ldb, double beta, cplx* C, int ldc, cplx* part, int nsplit) {
+    if (nsplit <= 1) return zgemm_tn(st, conjA, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, GEMM_FULL);
+    GemmArgs a;
+    a.A = A; a.B = B; a.C = part;
+    a.m = m; a.n = n; a.k = k;
+    a.lda = lda; a.ldb = ldb; a.ldc = n;
+    a.alpha = 1.0; a.beta = 0.0;
+    a.conjA = conjA ? 1 : 0;
+    a.uplo = GEMM_FULL;
+    int ks = (k + nsplit - 1) / nsplit;
+    ks = ((ks + BK - 1) / BK) * BK;
+    a.kslice = ks;
+    int nz = (k + ks - 1) / ks;
+    a.cslice = (long long)m * n;
+    int rc = launch(st, a, nz);
+    if (rc) return rc;
+    long long total = (long long)m * n;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part, nz, a.cslice, m, n, alpha, beta, C, ldc);
+    MSPDE_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace mspde
