@@ -1,12 +1,64 @@
-/* libmspde.so -- C ABI of the B200-native pCN hot path (placeholder header; filled in as entry points land). */
+/* libmspde.so -- C ABI of the B200-native pCN hot path of MCMC-MultiSPDE.
+ *
+ * The reference has no FFI layer: the path sits behind Python methods on CuPy arrays
+ * (SURVEY.md section 8b).  Each entry point below names the reference call site it replaces
+ * (paths relative to /root/reference).  Conventions:
+ *   - every matrix is row-major (C order) interleaved complex128 with an explicit leading dimension
+ *     (in complex elements); vectors are contiguous; all data pointers are DEVICE pointers unless the
+ *     name says host;
+ *   - every function returns int: 0 ok, >0 LAPACK-style info (host raises numpy.linalg.LinAlgError,
+ *     the only error Simulation.run catches, mcmc/image_cupy.py:969), <0 CUDA failure with the text
+ *     in mspde_last_error();
+ *   - work is enqueued on the context's stream; nothing synchronises unless stated.
+ */
 #ifndef MSPDE_H
 #define MSPDE_H
+#include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+typedef struct mspde_ctx mspde_ctx;
+
 const char* mspde_last_error(void);
+
+/* Context = sizes + borrowed fixed inputs + library-owned workspace (replaces the managed-memory pool and the
+ * temporaries of pCN._log_ratio, mcmc/image_cupy.py:834-835, 634-643). */
+int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n_layers, void* stream);
+int mspde_ctx_destroy(mspde_ctx* ctx);
+int mspde_ctx_set_stream(mspde_ctx* ctx, void* stream);
+/* H (M x N), H^H (N x M), HtH (N x N), y (M), D_diag (N), stdev_sym (N), delta = chol_epsilon*||HtH||_F
+ * (pCN.__init__ 436-452, set_chol_epsilon 473-478, Simulation.__init__ 869-880). */
+int mspde_ctx_set_inputs(mspde_ctx* ctx, const void* H, int ldH, const void* Hct, int ldHct, const void* HtH, int ldHtH,
+                         const double* y, const double* D_diag, const double* stdev_sym, double delta);
+int mspde_ctx_dims(mspde_ctx* ctx, int* out8_host);
+void* mspde_ctx_buffer(mspde_ctx* ctx, const char* name, int* ld_host);   /* debug/parity access to workspaces */
+int mspde_read_info(mspde_ctx* ctx, int reset);                           /* synchronises; returns device info flag */
+
+/* a1: FourierAnalysis_2D.__init__ index tables (mcmc/image_cupy.py:52-57, 63, 73-74); HOST arrays. */
+int mspde_index_maps(int n, int32_t* ix_host, int32_t* iy_host, int32_t* kmat_host, double* D_diag_host);
+/* a3: closed form of the _construct_U scatter (mcmc/util_cupy.py:426-442); HOST arrays N x N (bit-exact test). */
+int mspde_bttb_index_map(int n, int32_t* row_idx_host, int32_t* col_idx_host, uint8_t* mask_host);
+
+/* a2: sym2D(rfft2(exp(+-irfft2(u)))) -- FourierAnalysis_2D.constructMatexplicit up to the scatter (139-145). */
+int mspde_field_coeffs(mspde_ctx* ctx, const void* u_sym, void* coef_plus, void* coef_minus);
+/* a3+a4: L = (U[coef_plus]*D_diag - U[coef_minus])/sqrt_beta -- constructU + image_cupy.py:179, one fused pass. */
+int mspde_assemble_L(mspde_ctx* ctx, const void* coef_plus, const void* coef_minus, double sqrt_beta, void* L, int ldl);
+/* Lmatrix_2D.construct_from / construct_from_with_sqrt_beta (231-261). */
+int mspde_construct_L(mspde_ctx* ctx, const void* u_sym, double sqrt_beta, void* L, int ldl);
+
+/* a9: pCN._log_ratio (619-662, default branch); out3 (device) = {Phi, 0.5*||y@C||^2, sum log diag C}. */
+int mspde_phi(mspde_ctx* ctx, const void* L, int ldl, double* out3_dev);
+
+/* Building blocks (exported for the parity tests):
+ * zgemm_tn  : C = alpha*opA(A)^T*B + beta*C, A k x m, B k x n  (cuBLAS ZGEMM call sites 634, 639)
+ * zpotrf    : upper Cholesky A = U^H U                         (cuSOLVER ZPOTRF call sites 637, 642)
+ * ztrsm_uh  : B <- U^-H B                                      (cp.linalg.solve(c, H^H), 638) */
 int mspde_zgemm_tn(void* stream, int conjA, int m, int n, int k, double alpha, const void* A, int lda, const void* B,
                    int ldb, double beta, void* C, int ldc, int uplo, void* splitk_ws, int nsplit);
+int mspde_zpotrf_upper(void* stream, void* A, int lda, int n, void* winv, int* info_dev);
+int mspde_ztrsm_uh(void* stream, const void* U, int ldu, const void* winv, int n, void* B, int ldb, int ncols);
+
 #ifdef __cplusplus
 }
 #endif

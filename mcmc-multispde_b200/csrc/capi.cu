@@ -1,6 +1,8 @@
 // extern "C" boundary of libmspde.so -- declarations and reference citations live in include/mspde.h.
-#include "common.cuh"
+#include "context.cuh"
 #include <cstdarg>
+#include <cmath>
+#include <vector>
 #include "../../include/mspde.h"
 
 namespace mspde {
@@ -12,13 +14,178 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+static int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+template <typename T>
+static int dmalloc(T** p, size_t count) {
+    MSPDE_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    return 0;
+}
 }  // namespace mspde
 
 using namespace mspde;
 
+struct mspde_ctx {
+    Ctx c;
+    std::vector<void*> owned;
+};
+
+#define CTX_ALLOC(field, count)                                  \
+    do {                                                         \
+        if (dmalloc(&h->c.field, (count))) { mspde_ctx_destroy(h); return -1; } \
+        h->owned.push_back((void*)h->c.field);                   \
+    } while (0)
+
 extern "C" {
 
 const char* mspde_last_error(void) { return get_error(); }
+
+int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n_layers, void* stream) {
+    if (!out || n < 2 || n_ext < n || M < 1 || n_layers < 2) {
+        set_error("mspde_ctx_create: bad arguments (n=%d n_ext=%d M=%d n_layers=%d)", n, n_ext, M, n_layers);
+        return -1;
+    }
+    MSPDE_CUDA(cudaSetDevice(device));
+    mspde_ctx* h = new mspde_ctx();
+    Ctx& c = h->c;
+    c.device = device;
+    c.n = n; c.n_ext = n_ext; c.il = 2 * n - 1; c.N = c.il * c.il; c.n_ravel = 2 * n * n - 2 * n + 1;
+    c.m = 2 * n_ext - 1; c.M = M; c.n_layers = n_layers;
+    c.ldN = round_up(c.N, 8); c.ldM = round_up(M, 8);
+    c.stream = (cudaStream_t)stream;
+    const int N = c.N, m = c.m, il = c.il;
+    CTX_ALLOC(W, m);
+    CTX_ALLOC(T1, size_t(m) * il);
+    CTX_ALLOC(fp, size_t(m) * m);
+    CTX_ALLOC(fm, size_t(m) * m);
+    CTX_ALLOC(G, size_t(2) * m * n);
+    CTX_ALLOC(tp, size_t(il) * il);
+    CTX_ALLOC(tm, size_t(il) * il);
+    CTX_ALLOC(r, size_t(N) * c.ldN);
+    CTX_ALLOC(X, size_t(N) * c.ldM);
+    CTX_ALLOC(Q, size_t(M) * c.ldM);
+    CTX_ALLOC(winv, winv_elems(N > M ? N : M));
+    CTX_ALLOC(rowsq, M);
+    CTX_ALLOC(rowlog, M);
+    CTX_ALLOC(scal, 64);
+    CTX_ALLOC(info, 4);
+    CTX_ALLOC(vecN, size_t(4) * (N + M));
+    MSPDE_CUDA(cudaMemset(c.info, 0, 4 * sizeof(int)));
+    MSPDE_CUDA(cudaMemset(c.scal, 0, 64 * sizeof(double)));
+    std::vector<cplx> w(m);
+    for (int a = 0; a < m; ++a) {
+        const double ang = 2.0 * M_PI * double(a) / double(m);
+        w[a] = make_double2(cos(ang), sin(ang));
+    }
+    MSPDE_CUDA(cudaMemcpy(c.W, w.data(), m * sizeof(cplx), cudaMemcpyHostToDevice));
+    *out = h;
+    return 0;
+}
+
+int mspde_ctx_destroy(mspde_ctx* h) {
+    if (!h) return 0;
+    for (void* p : h->owned) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+int mspde_ctx_set_stream(mspde_ctx* h, void* stream) {
+    h->c.stream = (cudaStream_t)stream;
+    return 0;
+}
+
+int mspde_ctx_set_inputs(mspde_ctx* h, const void* H, int ldH, const void* Hct, int ldHct, const void* HtH, int ldHtH,
+                         const double* y, const double* D_diag, const double* stdev_sym, double delta) {
+    Ctx& c = h->c;
+    c.H = (const cplx*)H; c.ldH = ldH;
+    c.Hct = (const cplx*)Hct; c.ldHct = ldHct;
+    c.HtH = (const cplx*)HtH; c.ldHtH = ldHtH;
+    c.y = y; c.D_diag = D_diag; c.stdev_sym = stdev_sym; c.delta = delta;
+    return 0;
+}
+
+int mspde_ctx_dims(mspde_ctx* h, int* out8) {
+    const Ctx& c = h->c;
+    out8[0] = c.n; out8[1] = c.n_ext; out8[2] = c.il; out8[3] = c.N; out8[4] = c.n_ravel; out8[5] = c.m; out8[6] = c.M;
+    out8[7] = c.n_layers;
+    return 0;
+}
+
+void* mspde_ctx_buffer(mspde_ctx* h, const char* name, int* ld) {
+    Ctx& c = h->c;
+    if (!strcmp(name, "r")) { if (ld) *ld = c.ldN; return c.r; }
+    if (!strcmp(name, "X")) { if (ld) *ld = c.ldM; return c.X; }
+    if (!strcmp(name, "Q")) { if (ld) *ld = c.ldM; return c.Q; }
+    if (!strcmp(name, "tp")) { if (ld) *ld = c.il; return c.tp; }
+    if (!strcmp(name, "tm")) { if (ld) *ld = c.il; return c.tm; }
+    if (!strcmp(name, "fp")) { if (ld) *ld = c.m; return c.fp; }
+    if (!strcmp(name, "scal")) { if (ld) *ld = 1; return c.scal; }
+    if (!strcmp(name, "info")) { if (ld) *ld = 1; return c.info; }
+    set_error("mspde_ctx_buffer: unknown buffer '%s'", name);
+    return nullptr;
+}
+
+int mspde_index_maps(int n, int32_t* ix, int32_t* iy, int32_t* kmat, double* D_diag) {
+    // FourierAnalysis_2D.__init__ tables (host arrays): ix/iy il x il (row-major), Kmatrix 2 x N, D_diag N ('F' ravel)
+    const int il = 2 * n - 1, N = il * il;
+    const float two_pi = 2.0f * (float)M_PI;   // (2*util.PI)**2 is float32 arithmetic in the reference
+    const float c32 = two_pi * two_pi;
+    for (int r = 0; r < il; ++r)
+        for (int c = 0; c < il; ++c) {
+            if (ix) ix[r * il + c] = c - (n - 1);
+            if (iy) iy[r * il + c] = r - (n - 1);
+        }
+    for (int j = 0; j < N; ++j) {
+        const int kx = j / il - (n - 1), ky = j % il - (n - 1);
+        if (kmat) { kmat[j] = kx; kmat[N + j] = ky; }
+        if (D_diag) D_diag[j] = -(double)c32 * (double)(kx * kx + ky * ky);
+    }
+    return 0;
+}
+
+int mspde_bttb_index_map(int n, int32_t* row_idx, int32_t* col_idx, uint8_t* mask) {
+    // host restatement used by the bit-exactness test of the kernel's index arithmetic
+    const int il = 2 * n - 1, N = il * il;
+    for (int m = 0; m < N; ++m)
+        for (int c = 0; c < N; ++c) {
+            const int dij = m / il - c / il, dkl = m % il - c % il;
+            const size_t o = size_t(m) * N + c;
+            row_idx[o] = dkl + (n - 1);
+            col_idx[o] = dij + (n - 1);
+            mask[o] = (dij >= -(n - 1) && dij < n && dkl >= -(n - 1) && dkl < n) ? 1 : 0;
+        }
+    return 0;
+}
+
+int mspde_field_coeffs(mspde_ctx* h, const void* u_sym, void* coef_plus, void* coef_minus) {
+    return field_coeffs(&h->c, (const cplx*)u_sym, (cplx*)coef_plus, (cplx*)coef_minus);
+}
+
+int mspde_assemble_L(mspde_ctx* h, const void* coef_plus, const void* coef_minus, double sqrt_beta, void* L, int ldl) {
+    return assemble_L(&h->c, (const cplx*)coef_plus, (const cplx*)coef_minus, sqrt_beta, (cplx*)L, ldl);
+}
+
+int mspde_construct_L(mspde_ctx* h, const void* u_sym, double sqrt_beta, void* L, int ldl) {
+    int rc = field_coeffs(&h->c, (const cplx*)u_sym, h->c.tp, h->c.tm);
+    if (rc) return rc;
+    return assemble_L(&h->c, h->c.tp, h->c.tm, sqrt_beta, (cplx*)L, ldl);
+}
+
+int mspde_phi(mspde_ctx* h, const void* L, int ldl, double* out3_dev) {
+    return phi_eval(&h->c, (const cplx*)L, ldl, out3_dev);
+}
+
+int mspde_read_info(mspde_ctx* h, int reset) {
+    int v[4] = {0, 0, 0, 0};
+    if (cudaMemcpyAsync(v, h->c.info, sizeof(int), cudaMemcpyDeviceToHost, h->c.stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(h->c.stream) != cudaSuccess) {
+        set_error("stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    if (reset && v[0]) cudaMemsetAsync(h->c.info, 0, sizeof(int), h->c.stream);
+    return v[0];
+}
 
 int mspde_zgemm_tn(void* stream, int conjA, int m, int n, int k, double alpha, const void* A, int lda, const void* B,
                    int ldb, double beta, void* C, int ldc, int uplo, void* splitk_ws, int nsplit) {
@@ -27,6 +194,14 @@ int mspde_zgemm_tn(void* stream, int conjA, int m, int n, int k, double alpha, c
         return zgemm_tn_splitk(st, conjA != 0, m, n, k, alpha, (const cplx*)A, lda, (const cplx*)B, ldb, beta, (cplx*)C,
                                ldc, (cplx*)splitk_ws, nsplit);
     return zgemm_tn(st, conjA != 0, m, n, k, alpha, (const cplx*)A, lda, (const cplx*)B, ldb, beta, (cplx*)C, ldc, uplo);
+}
+
+int mspde_zpotrf_upper(void* stream, void* A, int lda, int n, void* winv, int* info_dev) {
+    return potrf_upper((cudaStream_t)stream, (cplx*)A, lda, n, (cplx*)winv, info_dev);
+}
+
+int mspde_ztrsm_uh(void* stream, const void* U, int ldu, const void* winv, int n, void* B, int ldb, int ncols) {
+    return trsm_uh((cudaStream_t)stream, (const cplx*)U, ldu, (const cplx*)winv, n, (cplx*)B, ldb, ncols);
 }
 
 }  // extern "C"

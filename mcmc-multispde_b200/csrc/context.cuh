@@ -1,0 +1,56 @@
+// Per-(device, n, n_ext, M, n_layers) context: problem sizes, borrowed fixed inputs, library-owned workspace.
+#pragma once
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace mspde {
+
+struct Ctx {
+    int device = 0;
+    int n = 0, n_ext = 0, il = 0, N = 0, n_ravel = 0, m = 0, M = 0, n_layers = 0;
+    int ldN = 0, ldM = 0;            // padded leading dimensions of the internal N- and M-wide workspaces
+    cudaStream_t stream = nullptr;
+
+    // fixed inputs, borrowed from the caller (device pointers, row-major)
+    const cplx* H = nullptr;   int ldH = 0;     // M x N   normalised tomography operator
+    const cplx* Hct = nullptr; int ldHct = 0;   // N x M   H^H
+    const cplx* HtH = nullptr; int ldHtH = 0;   // N x N   symmetrised H^H H / sigma^2
+    const double* y = nullptr;                  // M
+    const double* D_diag = nullptr;             // N
+    const double* stdev_sym = nullptr;          // N   layer-0 diagonal prior
+    double delta = 0.0;                         // Cholesky stabiliser  eps * ||HtH||_F
+
+    // field synthesis scratch
+    cplx* W = nullptr;        // m twiddles e^{2 pi i a / m}
+    cplx* T1 = nullptr;       // m x il
+    double* fp = nullptr;     // m x m   exp(+u)
+    double* fm = nullptr;     // m x m   exp(-u)
+    cplx* G = nullptr;        // 2 x m x n
+    cplx* tp = nullptr;       // il x il  sym2D(rfft2(exp(+u)))
+    cplx* tm = nullptr;       // il x il
+
+    // Phi workspace
+    cplx* r = nullptr;        // N x ldN
+    cplx* X = nullptr;        // N x ldM   Ht = c^-1 H^H
+    cplx* Q = nullptr;        // M x ldM
+    cplx* winv = nullptr;     // inverses of 64-blocks, sized for max(N, M)
+    double* rowsq = nullptr;  // M
+    double* rowlog = nullptr; // M
+    double* scal = nullptr;   // small device scalars (phi triples, logdet, flags)
+    int* info = nullptr;      // device LAPACK-style info
+
+    // LU / QR workspace
+    cplx* LUaug = nullptr;    // N x (ldN + 8)
+    void* lu_work = nullptr;
+    cplx* QRaug = nullptr;    // (M+N) x (ldN + 8)
+    void* qr_work = nullptr;
+    cplx* vecN = nullptr;     // scratch vectors
+};
+
+// assembly.cu
+int field_coeffs(Ctx* c, const cplx* u_sym, cplx* tp_out, cplx* tm_out);
+int assemble_L(Ctx* c, const cplx* tp, const cplx* tm, double sqrt_beta, cplx* L, int ldl);
+// phi.cu
+int phi_eval(Ctx* c, const cplx* L, int ldl, double* out3);   // out3 (device): phi, quad, logdet
+
+}  // namespace mspde

@@ -1,0 +1,177 @@
+// Blocked complex FP64 Cholesky (upper form, row-major:  A = U^H U) and the matching triangular solve
+// B <- U^-H B, both recursive so that almost all flops land in large-K zgemm_tn (DMMA) calls.
+//
+// Reference call sites: cp.linalg.cholesky at /root/reference/mcmc/image_cupy.py:637 and :642 (the
+// reference's lower factor c equals U^H here) and cp.linalg.solve(c, H^H) at :638.
+//
+// Leaves are 64 x 64 diagonal blocks handled by one CTA: the block is factorised with the trailing
+// matrix held in registers (one __syncthreads per column), then its triangular inverse is formed so
+// that the leaf solves become  X = inv(U11)^H B  -- again a zgemm_tn call (in place, one row tile).
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace mspde {
+
+namespace {
+
+constexpr int NB = LEAF;   // 64
+constexpr int SP = NB + 1; // padded pitch (complex) in shared memory
+
+// One CTA, 256 threads as a 16 x 16 grid; thread (ty, tx) owns elements (ty+16a, tx+16b), a,b in 0..3.
+__global__ void __launch_bounds__(256) potrf_diag_kernel(cplx* __restrict__ A, int lda, int nb, int goff,
+                                                         cplx* __restrict__ winv, int* __restrict__ info) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    cplx* S = reinterpret_cast<cplx*>(sm_raw);          // U (upper) after factorisation   [NB][SP]
+    cplx* X = S + NB * SP;                              // inverse                          [NB][SP]
+    __shared__ cplx rowbuf[2][NB];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+
+    cplx r[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int i = ty + 16 * a, j = tx + 16 * b;
+            cplx v = make_double2(0.0, 0.0);
+            if (i < nb && j < nb && j >= i) v = A[size_t(i) * lda + j];
+            if (i >= nb && i == j) v = make_double2(1.0, 0.0);   // identity padding for edge blocks
+            r[a][b] = v;
+        }
+    bool bad = false;
+    for (int k = 0; k < NB; ++k) {
+        const int ka = k >> 4, kr = k & 15;
+        if (ty == kr) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                if (a == ka) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) rowbuf[k & 1][tx + 16 * b] = r[a][b];
+                }
+        }
+        __syncthreads();
+        const double akk = rowbuf[k & 1][k].x;
+        if (!(akk > 0.0)) {
+            bad = true;   // not positive definite (or NaN): LAPACK zpotrf info = k+1
+            if (tid == 0) atomicCAS(info, 0, goff + k + 1);
+        }
+        const double d = sqrt(akk);
+        const double inv = 1.0 / d;
+        cplx vi[4], vj[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) vi[a] = cscale(rowbuf[k & 1][ty + 16 * a], inv);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) vj[b] = cscale(rowbuf[k & 1][tx + 16 * b], inv);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = ty + 16 * a;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = tx + 16 * b;
+                if (i == k) {
+                    if (j == k) r[a][b] = make_double2(d, 0.0);
+                    else if (j > k) r[a][b] = vj[b];
+                } else if (i > k && j >= i) {
+                    r[a][b] = cfnmac(vi[a], vj[b], r[a][b]);
+                }
+            }
+        }
+    }
+    (void)bad;
+    // publish U to shared memory and to A (upper triangle only)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int i = ty + 16 * a, j = tx + 16 * b;
+            S[i * SP + j] = r[a][b];
+            if (i < nb && j < nb && j >= i) A[size_t(i) * lda + j] = r[a][b];
+        }
+    __syncthreads();
+    // X = U^-1 by back substitution; 4 threads per column split the dot products
+    {
+        const int col = tid >> 2, part = tid & 3;
+        for (int i = NB - 1; i >= 0; --i) {
+            cplx s = make_double2(0.0, 0.0);
+            if (i < col) {
+                for (int k = i + 1 + part; k <= col; k += 4) s = cfma(S[i * SP + k], X[k * SP + col], s);
+            }
+            s.x += __shfl_xor_sync(0xffffffffu, s.x, 1);
+            s.y += __shfl_xor_sync(0xffffffffu, s.y, 1);
+            s.x += __shfl_xor_sync(0xffffffffu, s.x, 2);
+            s.y += __shfl_xor_sync(0xffffffffu, s.y, 2);
+            if (part == 0) {
+                const double uii = S[i * SP + i].x;   // diagonal of a Cholesky factor is real
+                cplx x;
+                if (i > col) x = make_double2(0.0, 0.0);
+                else if (i == col) x = make_double2(1.0 / uii, 0.0);
+                else x = make_double2(-s.x / uii, -s.y / uii);
+                X[i * SP + col] = x;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        int i = idx >> 6, j = idx & 63;
+        winv[idx] = X[i * SP + j];
+    }
+}
+
+int split(int n) {
+    int n1 = ((n / 2 + NB - 1) / NB) * NB;
+    if (n1 >= n) n1 -= NB;
+    if (n1 < NB) n1 = NB;
+    return n1;
+}
+
+bool g_attr = false;
+
+}  // namespace
+
+// B (n x ncols, row-major, ldb) <- U^-H B, U = upper n x n at `U` (ldu), winv = inverses of its 64-blocks.
+int trsm_uh(cudaStream_t st, const cplx* U, int ldu, const cplx* winv, int n, cplx* B, int ldb, int ncols) {
+    if (n <= 0 || ncols <= 0) return 0;
+    if (n <= NB) {
+        // leaf: X = inv(U11)^H B, in place (single row tile -> each CTA reads its whole B tile before writing)
+        return zgemm_tn(st, true, n, ncols, n, 1.0, winv, NB, B, ldb, 0.0, B, ldb, GEMM_FULL);
+    }
+    const int n1 = split(n);
+    int rc = trsm_uh(st, U, ldu, winv, n1, B, ldb, ncols);
+    if (rc) return rc;
+    // B2 -= U12^H X1
+    rc = zgemm_tn(st, true, n - n1, ncols, n1, -1.0, U + n1, ldu, B, ldb, 1.0, B + size_t(n1) * ldb, ldb, GEMM_FULL);
+    if (rc) return rc;
+    return trsm_uh(st, U + size_t(n1) * ldu + n1, ldu, winv + size_t(n1 / NB) * NB * NB, n - n1, B + size_t(n1) * ldb,
+                   ldb, ncols);
+}
+
+static int potrf_rec(cudaStream_t st, cplx* A, int lda, int n, int goff, cplx* winv, int* info) {
+    if (n <= NB) {
+        potrf_diag_kernel<<<1, 256, 2 * NB * SP * sizeof(cplx), st>>>(A, lda, n, goff, winv, info);
+        MSPDE_LAUNCH_CHECK();
+        return 0;
+    }
+    const int n1 = split(n);
+    int rc = potrf_rec(st, A, lda, n1, goff, winv, info);
+    if (rc) return rc;
+    cplx* A12 = A + n1;
+    cplx* A22 = A + size_t(n1) * lda + n1;
+    rc = trsm_uh(st, A, lda, winv, n1, A12, lda, n - n1);          // U12 = U11^-H A12
+    if (rc) return rc;
+    rc = zgemm_tn(st, true, n - n1, n - n1, n1, -1.0, A12, lda, A12, lda, 1.0, A22, lda, GEMM_UPPER);  // A22 -= U12^H U12
+    if (rc) return rc;
+    return potrf_rec(st, A22, lda, n - n1, goff + n1, winv + size_t(n1 / NB) * NB * NB, info);
+}
+
+// In-place upper Cholesky of the Hermitian matrix whose upper triangle is stored in A (row-major).
+// winv must hold ceil(n/64) * 64*64 complex.  *info (device) receives the first failing column (1-based), 0 if ok.
+int potrf_upper(cudaStream_t st, cplx* A, int lda, int n, cplx* winv, int* info) {
+    if (!g_attr) {
+        MSPDE_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(2 * NB * SP * sizeof(cplx))));
+        g_attr = true;
+    }
+    return potrf_rec(st, A, lda, n, 0, winv, info);
+}
+
+}  // namespace mspde
