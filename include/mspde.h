@@ -50,6 +50,46 @@ int mspde_construct_L(mspde_ctx* ctx, const void* u_sym, double sqrt_beta, void*
 /* a9: pCN._log_ratio (619-662, default branch); out3 (device) = {Phi, 0.5*||y@C||^2, sum log diag C}. */
 int mspde_phi(mspde_ctx* ctx, const void* L, int ldl, double* out3_dev);
 
+/* a5 + a8: cp.linalg.solve(L, w) (561, 681, 755, 785) and Lmatrix_2D.logDet (268-276; patch/norms.py:236-293).
+ * x (N) <- L^-1 rhs; logabsdet_dev (device double, may be NULL) <- log|det L| = sum log|diag| of the factor.
+ * L is not modified (it is copied into the workspace). */
+int mspde_solve(mspde_ctx* ctx, const void* L, int ldl, const void* rhs, void* x, double* logabsdet_dev);
+/* a11: util.lstsq(a, b) = reduced QR -> q^H b -> solve_triangular (mcmc/util_cupy.py:590-609,
+ * mcmc/extra_linalg.py:15-106); a is rows x cols (rows >= cols, within the context's (M+N) x N workspace). */
+int mspde_lstsq(mspde_ctx* ctx, const void* a, int lda, int rows, int cols, const void* b, void* x);
+/* v = lstsq(vstack(H, L), rhs) with rhs of length M+N (image_cupy.py:596-599). */
+int mspde_gibbs_lstsq(mspde_ctx* ctx, const void* L, int ldl, const void* rhs, void* v);
+
+/* a6-a12: pCN.one_step (553-617) with injected noise, accept decision on the device.
+ * All pointers inside the structs are device pointers except sqrt_betas (host). */
+typedef struct {
+    int n_layers;
+    double beta, betaZ;             /* pCN step (host-managed adaptation, 528-540) */
+    const double* sqrt_betas;       /* host, n_layers */
+    void** noise_cur;               /* host arrays of n_layers device pointers, each N complex */
+    void** noise_new;
+    void** u_cur;                   /* current_sample_sym */
+    void** u_new;                   /* new_sample_sym */
+    void** L_cur;                   /* per layer k >= 1: N x ldl; entry 0 unused */
+    void** L_latest;
+    int ldl;
+    int phi_cur_valid;              /* scal cache holds Phi(L_cur[last]) from a previous step */
+} mspde_chain;
+
+typedef struct {
+    const void** w_half;            /* host array of n_layers-1 device pointers (n_ravel complex each) */
+    const void* w_last;             /* n_ravel complex: last layer's Gibbs noise */
+    const double* e;                /* M real */
+    double log_u;                   /* log of the accept uniform */
+} mspde_step_noise;
+
+enum { MSPDE_STEP_CACHE_PHI_CUR = 1, MSPDE_STEP_SKIP_GIBBS = 2 };
+
+/* out_dev (device, 4 doubles) <- {accepted (0/1), logRatio, Phi_cur, Phi_new}; record_dev (optional) <-
+ * n_layers x n_ravel current half samples (Layer.record_sample, 792-795). */
+int mspde_pcn_step(mspde_ctx* ctx, const mspde_chain* chain, const mspde_step_noise* noise, int flags, double* out_dev,
+                   void* record_dev);
+
 /* Building blocks (exported for the parity tests):
  * zgemm_tn  : C = alpha*opA(A)^T*B + beta*C, A k x m, B k x n  (cuBLAS ZGEMM call sites 634, 639)
  * zpotrf    : upper Cholesky A = U^H U                         (cuSOLVER ZPOTRF call sites 637, 642)

@@ -71,6 +71,14 @@ int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n
     CTX_ALLOC(scal, 64);
     CTX_ALLOC(info, 4);
     CTX_ALLOC(vecN, size_t(4) * (N + M));
+    c.ldA = round_up(N + 1, 8);
+    CTX_ALLOC(QRaug, size_t(M + N) * c.ldA);
+    {
+        unsigned char* w = nullptr;
+        if (dmalloc(&w, qr_work_bytes(M + N, N))) { mspde_ctx_destroy(h); return -1; }
+        h->owned.push_back(w);
+        c.qr_work = w;
+    }
     MSPDE_CUDA(cudaMemset(c.info, 0, 4 * sizeof(int)));
     MSPDE_CUDA(cudaMemset(c.scal, 0, 64 * sizeof(double)));
     std::vector<cplx> w(m);
@@ -174,6 +182,27 @@ int mspde_construct_L(mspde_ctx* h, const void* u_sym, double sqrt_beta, void* L
 
 int mspde_phi(mspde_ctx* h, const void* L, int ldl, double* out3_dev) {
     return phi_eval(&h->c, (const cplx*)L, ldl, out3_dev);
+}
+
+int mspde_solve(mspde_ctx* h, const void* L, int ldl, const void* rhs, void* x, double* logabsdet_dev) {
+    return solve_L(&h->c, (const cplx*)L, ldl, (const cplx*)rhs, (cplx*)x, logabsdet_dev ? logabsdet_dev : h->c.scal + 20);
+}
+
+int mspde_lstsq(mspde_ctx* h, const void* a, int lda, int rows, int cols, const void* b, void* x) {
+    return lstsq_general(&h->c, (const cplx*)a, lda, rows, cols, (const cplx*)b, (cplx*)x);
+}
+
+int mspde_gibbs_lstsq(mspde_ctx* h, const void* L, int ldl, const void* rhs, void* v) {
+    return gibbs_lstsq(&h->c, (const cplx*)L, ldl, (const cplx*)rhs, (cplx*)v);
+}
+
+int mspde_pcn_step(mspde_ctx* h, const mspde_chain* chain, const mspde_step_noise* noise, int flags, double* out_dev,
+                   void* record_dev) {
+    if (!chain || !noise || chain->n_layers != h->c.n_layers) {
+        set_error("mspde_pcn_step: chain/noise missing or n_layers mismatch");
+        return -1;
+    }
+    return pcn_step(&h->c, chain, noise, flags, out_dev, (cplx*)record_dev);
 }
 
 int mspde_read_info(mspde_ctx* h, int reset) {

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "linalg.cuh"
+#include "../../include/mspde.h"
 
 namespace mspde {
 
@@ -39,13 +40,18 @@ struct Ctx {
     double* scal = nullptr;   // small device scalars (phi triples, logdet, flags)
     int* info = nullptr;      // device LAPACK-style info
 
-    // LU / QR workspace
-    cplx* LUaug = nullptr;    // N x (ldN + 8)
-    void* lu_work = nullptr;
-    cplx* QRaug = nullptr;    // (M+N) x (ldN + 8)
+    // QR workspace (Gibbs least squares and the dense solves L x = w)
+    cplx* QRaug = nullptr;    // (M+N) x ldA,  ldA = round8(N+1)
+    int ldA = 0;
     void* qr_work = nullptr;
     cplx* vecN = nullptr;     // scratch vectors
 };
+
+// pcn.cu
+int solve_L(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* x, double* logabsdet);
+int gibbs_lstsq(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* v);
+int lstsq_general(Ctx* c, const cplx* A, int lda, int rows, int cols, const cplx* b, cplx* x);
+int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flags, double* out_dev, cplx* record_dev);
 
 // assembly.cu
 int field_coeffs(Ctx* c, const cplx* u_sym, cplx* tp_out, cplx* tm_out);

@@ -1,0 +1,339 @@
+// Blocked Householder QR least squares (row-major complex128) for the Gibbs draw of the last layer and for the
+// dense solves L x = w of the middle layers.
+//
+// Reference call sites: util.lstsq = cupy.linalg.qr -> q^H b -> solve_triangular
+// (/root/reference/mcmc/util_cupy.py:590-609, /root/reference/mcmc/extra_linalg.py:15-106) and
+// cp.linalg.solve(L, w) (/root/reference/mcmc/image_cupy.py:561).  No explicit Q is formed: the right-hand side
+// travels as an extra column of the matrix, so Q^H b falls out of the trailing updates.
+//
+// Per 64-column panel:
+//   1. qr_panel_kernel   cooperative launch, each CTA keeps a slab of panel rows in shared memory; one grid
+//                        barrier per column: the column norm and all v^H a_j' products are reduced together
+//   2. V^H V (split-K zgemm_tn) -> larft_kernel builds the compact-WY factor T
+//   3. W = V^H A2 (split-K zgemm_tn), W <- T^H W (in-place leaf zgemm_tn), A2 -= V W (zgemm_tn, K = 64)
+#include <cooperative_groups.h>
+#include "linalg.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mspde {
+
+namespace {
+
+constexpr int PW = 64;           // panel width
+constexpr int SPITCH = PW + 1;   // shared-memory row pitch (complex)
+constexpr int MAXG = 148;        // CTAs of the cooperative panel kernel (one per SM)
+constexpr size_t SMALL_SMEM = (size_t(PW) * (PW + 1) + PW) * sizeof(cplx);
+
+struct QrWork {
+    cplx* V;      // rows x PW   explicit reflectors (unit diagonal, zeros above)
+    cplx* Vt;     // PW x ldvt   transposed copy
+    cplx* W;      // PW x ldw
+    cplx* part;   // split-K partials
+    cplx* Gm;     // PW x PW  V^H V
+    cplx* T;      // PW x PW  compact WY factor
+    cplx* tau;    // PW
+    cplx* dots;   // 2 x MAXG x PW   per-CTA partial dot products (double buffered)
+    cplx* currow; // 2 x PW          current diagonal row (double buffered)
+    int ldvt, ldw, nsplit;
+};
+
+size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
+
+// Panel: A[c0 + (0..mp-1)][c0 + (0..pw-1)], pw <= PW pivot columns.
+__global__ void __launch_bounds__(256) qr_panel_kernel(cplx* __restrict__ A, int lda, int mp, int pw, int slab,
+                                                       cplx* __restrict__ V, cplx* __restrict__ Vt, int ldvt,
+                                                       cplx* __restrict__ tau_out, cplx* __restrict__ dots,
+                                                       cplx* __restrict__ currow, double* __restrict__ logabs) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    cplx* S = reinterpret_cast<cplx*>(sm_raw);   // [slab][SPITCH]
+    __shared__ cplx red[4][PW];
+    __shared__ cplx sdot[PW];
+    __shared__ cplx srow[PW];
+    const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+    const int G = gridDim.x;
+    const int row0 = blockIdx.x * slab;                 // first panel-local row of this slab
+    const int nrow = max(0, min(slab, mp - row0));
+
+    for (int idx = tid; idx < nrow * PW; idx += 256) {
+        const int i = idx >> 6, j = idx & 63;
+        S[i * SPITCH + j] = (j < pw) ? A[size_t(row0 + i) * lda + j] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+
+    for (int j = 0; j < pw; ++j) {
+        const int buf = j & 1;
+        // ---- partial dots over rows strictly below the diagonal row j:  sum_i conj(a[i][j]) a[i][j'] , j' >= j
+        cplx acc = make_double2(0.0, 0.0);
+        if (tx >= j && tx < pw) {
+            const int lo = max(0, j + 1 - row0);
+            for (int i = lo + ty; i < nrow; i += 4) acc = cfmac(S[i * SPITCH + j], S[i * SPITCH + tx], acc);
+        }
+        red[ty][tx] = acc;
+        __syncthreads();
+        if (ty == 0) {
+            cplx s = cadd(cadd(red[0][tx], red[1][tx]), cadd(red[2][tx], red[3][tx]));
+            dots[(size_t(buf) * MAXG + blockIdx.x) * PW + tx] = s;
+            if (j >= row0 && j < row0 + nrow) currow[buf * PW + tx] = S[(j - row0) * SPITCH + tx];
+        }
+        grid.sync();
+        // ---- every CTA reduces the G partials in the same fixed order
+        {
+            cplx s = make_double2(0.0, 0.0);
+            for (int c = ty; c < G; c += 4) s = cadd(s, dots[(size_t(buf) * MAXG + c) * PW + tx]);
+            red[ty][tx] = s;
+        }
+        __syncthreads();
+        if (ty == 0) {
+            sdot[tx] = cadd(cadd(red[0][tx], red[1][tx]), cadd(red[2][tx], red[3][tx]));
+            srow[tx] = currow[buf * PW + tx];
+        }
+        __syncthreads();
+        // ---- zlarfg: alpha = a_jj, beta = -sign(Re alpha) * sqrt(|alpha|^2 + xnorm^2), tau = (beta - alpha)/beta
+        const cplx alpha = srow[j];
+        const double xn2 = sdot[j].x;
+        cplx tau = make_double2(0.0, 0.0), scale = make_double2(0.0, 0.0);
+        double beta = alpha.x;
+        const bool trivial = (xn2 == 0.0 && alpha.y == 0.0);
+        if (!trivial) {
+            beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xn2), alpha.x);
+            tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
+            scale = cdiv(make_double2(1.0, 0.0), make_double2(alpha.x - beta, alpha.y));
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+            tau_out[j] = tau;
+            if (logabs) *logabs += log(fabs(beta));
+        }
+        // w_j' = v^H a_j' = a[j][j'] + conj(scale) * dot_j' ; coefficient applied to rows: conj(tau) * w_j'
+        cplx coef = make_double2(0.0, 0.0);
+        if (tx > j && tx < pw && !trivial) {
+            cplx w = cadd(srow[tx], cmulc(scale, sdot[tx]));
+            coef = cmulc(tau, w);
+        }
+        // ---- apply H_j^H to the slab and store v_j in column j
+        {
+            const int lo = max(0, j - row0);
+            for (int i = lo + ty; i < nrow; i += 4) {
+                const int gi = row0 + i;
+                if (gi == j) {
+                    if (tx > j && tx < pw) S[i * SPITCH + tx] = csub(S[i * SPITCH + tx], coef);
+                } else {
+                    const cplx vij = cmul(S[i * SPITCH + j], scale);
+                    if (tx > j && tx < pw) S[i * SPITCH + tx] = cfnma(coef, vij, S[i * SPITCH + tx]);
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const int lo = max(0, j - row0);
+            for (int i = lo + tid; i < nrow; i += 256) {
+                const int gi = row0 + i;
+                if (gi == j) S[i * SPITCH + j] = make_double2(beta, 0.0);
+                else S[i * SPITCH + j] = trivial ? make_double2(0.0, 0.0) : cmul(S[i * SPITCH + j], scale);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- write back: R on/above the diagonal into A (reflector storage below it), explicit V and V^T to workspace
+    for (int idx = tid; idx < nrow * PW; idx += 256) {
+        const int i = idx >> 6, j = idx & 63;
+        const int gi = row0 + i;
+        const cplx v = S[i * SPITCH + j];
+        if (j < pw) A[size_t(gi) * lda + j] = v;
+        cplx e = make_double2(0.0, 0.0);
+        if (j < pw) {
+            if (gi > j) e = v;
+            else if (gi == j) e = make_double2(1.0, 0.0);
+        }
+        V[size_t(gi) * PW + j] = e;
+    }
+    for (int idx = tid; idx < nrow * PW; idx += 256) {
+        const int j = idx / nrow, i = idx % nrow;
+        const int gi = row0 + i;
+        cplx e = make_double2(0.0, 0.0);
+        if (j < pw) {
+            if (gi > j) e = S[i * SPITCH + j];
+            else if (gi == j) e = make_double2(1.0, 0.0);
+        }
+        Vt[size_t(j) * ldvt + gi] = e;
+    }
+}
+
+// T[j][j] = tau_j ; T[0:j, j] = -tau_j * T[0:j,0:j] * (V^H V)[0:j, j]      (zlarft, forward, columnwise)
+__global__ void __launch_bounds__(PW) larft_kernel(const cplx* __restrict__ Gm, const cplx* __restrict__ tau, int pw,
+                                                   cplx* __restrict__ T) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    cplx (*sT)[PW + 1] = reinterpret_cast<cplx (*)[PW + 1]>(sm_raw);
+    cplx* col = reinterpret_cast<cplx*>(sm_raw) + PW * (PW + 1);
+    const int a = threadIdx.x;
+    for (int b = 0; b < PW; ++b) sT[a][b] = make_double2(0.0, 0.0);
+    __syncthreads();
+    for (int j = 0; j < pw; ++j) {
+        const cplx tj = tau[j];
+        col[a] = (a < j) ? Gm[a * PW + j] : make_double2(0.0, 0.0);
+        __syncthreads();
+        if (a < j) {
+            cplx s = make_double2(0.0, 0.0);
+            for (int b = a; b < j; ++b) s = cfma(sT[a][b], col[b], s);
+            sT[a][j] = cmul(make_double2(-tj.x, -tj.y), s);
+        } else if (a == j) {
+            sT[a][j] = tj;
+        }
+        __syncthreads();
+    }
+    for (int b = 0; b < PW; ++b) T[a * PW + b] = sT[a][b];
+}
+
+// x_blk = R_bb^-1 d_blk for one 64-block (single CTA), R upper; d lives in column `dcol` of the same matrix
+__global__ void __launch_bounds__(64) trsv_diag_kernel(const cplx* __restrict__ A, int lda, int b0, int nb, int dcol,
+                                                       cplx* __restrict__ x) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    cplx (*R)[PW + 1] = reinterpret_cast<cplx (*)[PW + 1]>(sm_raw);
+    cplx* xs = reinterpret_cast<cplx*>(sm_raw) + PW * (PW + 1);
+    const int t = threadIdx.x;
+    for (int i = 0; i < nb; ++i)
+        if (t < nb) R[i][t] = A[size_t(b0 + i) * lda + b0 + t];
+    if (t < nb) xs[t] = A[size_t(b0 + t) * lda + dcol];
+    __syncthreads();
+    for (int i = nb - 1; i >= 0; --i) {
+        if (t == i) xs[i] = cdiv(xs[i], R[i][i]);
+        __syncthreads();
+        if (t < i) xs[t] = cfnma(R[t][i], xs[i], xs[t]);
+        __syncthreads();
+    }
+    if (t < nb) x[b0 + t] = xs[t];
+}
+
+// d[i] -= sum_{k in block} R[i][b0+k] x[b0+k] for all rows i < b0 (one warp per row)
+__global__ void __launch_bounds__(256) trsv_update_kernel(cplx* __restrict__ A, int lda, int b0, int nb, int dcol,
+                                                          const cplx* __restrict__ x) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= b0) return;
+    cplx s = make_double2(0.0, 0.0);
+    for (int k = lane; k < nb; k += 32) s = cfma(A[size_t(i) * lda + b0 + k], x[b0 + k], s);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+    }
+    if (lane == 0) {
+        cplx* d = A + size_t(i) * lda + dcol;
+        *d = csub(*d, s);
+    }
+}
+
+QrWork carve(void* work, int rows, int cols) {
+    QrWork w;
+    unsigned char* p = reinterpret_cast<unsigned char*>(work);
+    auto take = [&](size_t bytes) { void* q = p; p += align_up(bytes); return q; };
+    w.ldvt = (rows + 7) / 8 * 8;
+    w.ldw = (cols + 1 + 7) / 8 * 8;
+    w.nsplit = 6;
+    w.V = (cplx*)take(size_t(rows) * PW * sizeof(cplx));
+    w.Vt = (cplx*)take(size_t(PW) * w.ldvt * sizeof(cplx));
+    w.W = (cplx*)take(size_t(PW) * w.ldw * sizeof(cplx));
+    w.part = (cplx*)take(size_t(w.nsplit + 1) * PW * w.ldw * sizeof(cplx));
+    w.Gm = (cplx*)take(size_t(PW) * PW * sizeof(cplx));
+    w.T = (cplx*)take(size_t(PW) * PW * sizeof(cplx));
+    w.tau = (cplx*)take(size_t(PW) * sizeof(cplx));
+    w.dots = (cplx*)take(size_t(2) * MAXG * PW * sizeof(cplx));
+    w.currow = (cplx*)take(size_t(2) * PW * sizeof(cplx));
+    return w;
+}
+
+bool g_attr = false;
+
+}  // namespace
+
+size_t qr_work_bytes(int rows, int cols) {
+    const size_t ldvt = (rows + 7) / 8 * 8, ldw = (cols + 1 + 7) / 8 * 8;
+    size_t b = 0;
+    b += align_up(size_t(rows) * PW * sizeof(cplx));
+    b += align_up(size_t(PW) * ldvt * sizeof(cplx));
+    b += align_up(size_t(PW) * ldw * sizeof(cplx));
+    b += align_up(size_t(7) * PW * ldw * sizeof(cplx));
+    b += 3 * align_up(size_t(PW) * PW * sizeof(cplx));
+    b += align_up(size_t(2) * MAXG * PW * sizeof(cplx));
+    b += align_up(size_t(2) * PW * sizeof(cplx));
+    return b + 4096;
+}
+
+// Householder QR of the leading `cols` columns of Aaug (rows x (cols + naug)), trailing columns get Q^H applied.
+// logabs (device, optional) accumulates sum log |r_jj|.
+static int init_attrs() {
+    if (!g_attr) {
+        MSPDE_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MSPDE_CUDA(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
+        MSPDE_CUDA(cudaFuncSetAttribute(trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
+        g_attr = true;
+    }
+    return 0;
+}
+
+int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs) {
+    if (init_attrs()) return -1;
+    QrWork w = carve(work, rows, cols);
+    if (logabs) MSPDE_CUDA(cudaMemsetAsync(logabs, 0, sizeof(double), st));
+    const int ntot = cols + naug;
+    for (int c0 = 0; c0 < cols; c0 += PW) {
+        const int pw = min(PW, cols - c0);
+        const int mp = rows - c0;
+        int G = min(MAXG, (mp + 63) / 64);
+        int slab = (mp + G - 1) / G;
+        G = (mp + slab - 1) / slab;
+        const size_t smem = size_t(slab) * SPITCH * sizeof(cplx);
+        if (smem > 200 * 1024) {
+            set_error("geqrf_aug: panel slab of %d rows does not fit in shared memory", slab);
+            return -1;
+        }
+        cplx* Ap = A + size_t(c0) * lda + c0;
+        cplx* V = w.V; cplx* Vt = w.Vt; int ldvt = w.ldvt; cplx* tau = w.tau; cplx* dots = w.dots; cplx* currow = w.currow;
+        int mp_ = mp, pw_ = pw, slab_ = slab, lda_ = lda;
+        double* la = logabs;
+        void* args[] = {&Ap, &lda_, &mp_, &pw_, &slab_, &V, &Vt, &ldvt, &tau, &dots, &currow, &la};
+        MSPDE_CUDA(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(G), dim3(256), args, smem, st));
+        const int n2 = ntot - (c0 + pw);
+        if (n2 <= 0) continue;
+        // T from V^H V
+        int rc = zgemm_tn_splitk(st, true, PW, PW, mp, 1.0, w.V, PW, w.V, PW, 0.0, w.Gm, PW, w.part, w.nsplit);
+        if (rc) return rc;
+        larft_kernel<<<1, PW, SMALL_SMEM, st>>>(w.Gm, w.tau, pw, w.T);
+        MSPDE_LAUNCH_CHECK();
+        cplx* A2 = Ap + pw;
+        // W = V^H A2
+        rc = zgemm_tn_splitk(st, true, PW, n2, mp, 1.0, w.V, PW, A2, lda, 0.0, w.W, w.ldw, w.part, w.nsplit);
+        if (rc) return rc;
+        // W <- T^H W (in place: single row tile)
+        rc = zgemm_tn(st, true, PW, n2, PW, 1.0, w.T, PW, w.W, w.ldw, 0.0, w.W, w.ldw, GEMM_FULL);
+        if (rc) return rc;
+        // A2 -= V W
+        rc = zgemm_tn(st, false, mp, n2, PW, -1.0, w.Vt, w.ldvt, w.W, w.ldw, 1.0, A2, lda, GEMM_FULL);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// x <- R^-1 d, R = upper triangle of A[0:n,0:n], d = column dcol of A
+int trsv_upper_aug(cudaStream_t st, cplx* A, int lda, int n, int dcol, cplx* x) {
+    if (init_attrs()) return -1;
+    for (int b0 = ((n - 1) / PW) * PW; b0 >= 0; b0 -= PW) {
+        const int nb = min(PW, n - b0);
+        trsv_diag_kernel<<<1, 64, SMALL_SMEM, st>>>(A, lda, b0, nb, dcol, x);
+        MSPDE_LAUNCH_CHECK();
+        if (b0 > 0) {
+            trsv_update_kernel<<<(b0 + 7) / 8, 256, 0, st>>>(A, lda, b0, nb, dcol, x);
+            MSPDE_LAUNCH_CHECK();
+        }
+    }
+    return 0;
+}
+
+int lstsq_qr_aug(cudaStream_t st, cplx* Aaug, int lda, int rows, int cols, void* work, cplx* x, double* logabs) {
+    int rc = geqrf_aug(st, Aaug, lda, rows, cols, 1, work, logabs);
+    if (rc) return rc;
+    return trsv_upper_aug(st, Aaug, lda, cols, cols, x);
+}
+
+}  // namespace mspde

@@ -1,0 +1,195 @@
+// a6-a12: the pCN step around the dense kernels -- non-centred proposals, dense solves, accept/reject and the
+// Gibbs draw of the last layer (pCN.one_step, /root/reference/mcmc/image_cupy.py:553-617).
+// Everything is enqueued on the context stream; the accept decision is taken on the device, so the host only
+// synchronises when it wants the flags.
+#include "context.cuh"
+#include "../../include/mspde.h"
+
+namespace mspde {
+
+namespace {
+
+__device__ __forceinline__ cplx sym_at(const cplx* __restrict__ half, int j, int nr) {
+    // util.symmetrize: concat(conj(half[:0:-1]), half)  (/root/reference/mcmc/util_cupy.py:201-204)
+    if (j >= nr - 1) return half[j - (nr - 1)];
+    cplx v = half[(nr - 1) - j];
+    return make_double2(v.x, -v.y);
+}
+
+// Layer.sample_non_centered (image_cupy.py:789-790) fused with the layer-0 diagonal map (563)
+__global__ void propose_kernel(const cplx* __restrict__ noise_cur, const cplx* __restrict__ w_half, double beta,
+                               double betaZ, int N, int nr, cplx* __restrict__ noise_new,
+                               const double* __restrict__ stdev_sym, cplx* __restrict__ u_new0) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const cplx w = sym_at(w_half, j, nr);
+    const cplx c = noise_cur[j];
+    cplx v;
+    v.x = betaZ * c.x + beta * w.x;
+    v.y = betaZ * c.y + beta * w.y;
+    noise_new[j] = v;
+    if (stdev_sym) {
+        const double s = stdev_sym[j];
+        u_new0[j] = make_double2(s * v.x, s * v.y);
+    }
+}
+
+// logRatio = phi_cur - phi_new ; accepted = logRatio > log_u  (image_cupy.py:571-573)
+__global__ void accept_kernel(const double* __restrict__ phi_cur3, const double* __restrict__ phi_new3, double log_u,
+                              double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double lr = phi_cur3[0] - phi_new3[0];
+        out[0] = (lr > log_u) ? 1.0 : 0.0;
+        out[1] = lr;
+        out[2] = phi_cur3[0];
+        out[3] = phi_new3[0];
+    }
+}
+
+// dst <- src when *flag != 0  (Layer.update_current_sample, image_cupy.py:802-807; set_current_L_to_latest 279-280)
+__global__ void cond_copy_kernel(const double* __restrict__ flag, const double2* __restrict__ src,
+                                 double2* __restrict__ dst, size_t count) {
+    if (*flag == 0.0) return;
+    size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    for (; i < count; i += stride) dst[i] = src[i];
+}
+
+__global__ void cond_copy_scalar_kernel(const double* __restrict__ flag, const double* __restrict__ src,
+                                        double* __restrict__ dst, int count) {
+    if (*flag == 0.0) return;
+    if (threadIdx.x < count) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+// column `col` of Aaug <- b
+__global__ void set_col_kernel(cplx* __restrict__ A, int lda, int col, const cplx* __restrict__ b, int rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) A[size_t(i) * lda + col] = b[i];
+}
+
+// column `col` of the stacked Gibbs system <- [y - e ; -noise_new]   (image_cupy.py:449, 584-586, 597)
+__global__ void gibbs_rhs_kernel(cplx* __restrict__ A, int lda, int col, const double* __restrict__ y,
+                                 const double* __restrict__ e, const cplx* __restrict__ noise, int M, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) A[size_t(i) * lda + col] = make_double2(y[i] - e[i], 0.0);
+    else if (i < M + N) {
+        const cplx w = noise[i - M];
+        A[size_t(i) * lda + col] = make_double2(0.0 - w.x, 0.0 - w.y);
+    }
+}
+
+__global__ void record_kernel(const cplx* __restrict__ u_sym, int nr, cplx* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nr) out[j] = u_sym[nr - 1 + j];   // current_sample = sym[n_ravel-1:]  (image_cupy.py:564, 794)
+}
+
+int copy2d(cudaStream_t st, cplx* dst, int ldd, const cplx* src, int lds, int rows, int cols) {
+    MSPDE_CUDA(cudaMemcpy2DAsync(dst, size_t(ldd) * sizeof(cplx), src, size_t(lds) * sizeof(cplx),
+                                 size_t(cols) * sizeof(cplx), rows, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // namespace
+
+// x = L^-1 rhs through Householder QR of L (backward stable, no pivoting needed); logabsdet = sum log |r_jj|.
+int solve_L(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* x, double* logabsdet) {
+    const int N = c->N;
+    int rc = copy2d(c->stream, c->QRaug, c->ldA, L, ldl, N, N);
+    if (rc) return rc;
+    set_col_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(c->QRaug, c->ldA, N, rhs, N);
+    MSPDE_LAUNCH_CHECK();
+    return lstsq_qr_aug(c->stream, c->QRaug, c->ldA, N, N, c->qr_work, x, logabsdet);
+}
+
+int lstsq_general(Ctx* c, const cplx* A, int lda, int rows, int cols, const cplx* b, cplx* x) {
+    if (rows > c->M + c->N || cols > c->N || rows < cols) {
+        set_error("mspde_lstsq: shape %d x %d exceeds the context workspace (%d x %d)", rows, cols, c->M + c->N, c->N);
+        return -1;
+    }
+    int rc = copy2d(c->stream, c->QRaug, c->ldA, A, lda, rows, cols);
+    if (rc) return rc;
+    set_col_kernel<<<(rows + 255) / 256, 256, 0, c->stream>>>(c->QRaug, c->ldA, cols, b, rows);
+    MSPDE_LAUNCH_CHECK();
+    return lstsq_qr_aug(c->stream, c->QRaug, c->ldA, rows, cols, c->qr_work, x, nullptr);
+}
+
+// v = argmin || [H; L] v - rhs ||  (image_cupy.py:596-599)
+int gibbs_lstsq(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* v) {
+    const int N = c->N, M = c->M;
+    int rc = copy2d(c->stream, c->QRaug, c->ldA, c->H, c->ldH, M, N);
+    if (rc) return rc;
+    rc = copy2d(c->stream, c->QRaug + size_t(M) * c->ldA, c->ldA, L, ldl, N, N);
+    if (rc) return rc;
+    set_col_kernel<<<(M + N + 255) / 256, 256, 0, c->stream>>>(c->QRaug, c->ldA, N, rhs, M + N);
+    MSPDE_LAUNCH_CHECK();
+    return lstsq_qr_aug(c->stream, c->QRaug, c->ldA, M + N, N, c->qr_work, v, nullptr);
+}
+
+int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flags, double* out_dev, cplx* record_dev) {
+    cudaStream_t st = c->stream;
+    const int K = ch->n_layers, N = c->N, M = c->M, nr = c->n_ravel;
+    const int nb = (N + 255) / 256;
+    double* phi_cur3 = c->scal + 8;
+    double* phi_new3 = c->scal + 12;
+    int rc;
+    for (int k = 0; k < K - 1; ++k) {
+        propose_kernel<<<nb, 256, 0, st>>>((const cplx*)ch->noise_cur[k], (const cplx*)nz->w_half[k], ch->beta, ch->betaZ, N,
+                                           nr, (cplx*)ch->noise_new[k], k == 0 ? c->stdev_sym : nullptr,
+                                           (cplx*)ch->u_new[0]);
+        MSPDE_LAUNCH_CHECK();
+        if (k > 0) {
+            rc = field_coeffs(c, (const cplx*)ch->u_new[k - 1], c->tp, c->tm);
+            if (rc) return rc;
+            rc = assemble_L(c, c->tp, c->tm, ch->sqrt_betas[k], (cplx*)ch->L_latest[k], ch->ldl);
+            if (rc) return rc;
+            rc = solve_L(c, (const cplx*)ch->L_latest[k], ch->ldl, (const cplx*)ch->noise_new[k], (cplx*)ch->u_new[k],
+                         c->scal + 20);
+            if (rc) return rc;
+        }
+    }
+    const bool cached = (flags & MSPDE_STEP_CACHE_PHI_CUR) && ch->phi_cur_valid;
+    if (!cached) {
+        rc = phi_eval(c, (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3);
+        if (rc) return rc;
+    }
+    rc = field_coeffs(c, (const cplx*)ch->u_new[K - 2], c->tp, c->tm);
+    if (rc) return rc;
+    rc = assemble_L(c, c->tp, c->tm, ch->sqrt_betas[K - 1], (cplx*)ch->L_latest[K - 1], ch->ldl);
+    if (rc) return rc;
+    rc = phi_eval(c, (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3);
+    if (rc) return rc;
+    accept_kernel<<<1, 32, 0, st>>>(phi_cur3, phi_new3, nz->log_u, out_dev);
+    MSPDE_LAUNCH_CHECK();
+    for (int k = 0; k < K; ++k) {
+        cond_copy_kernel<<<nb, 256, 0, st>>>(out_dev, (const double2*)ch->u_new[k], (double2*)ch->u_cur[k], N);
+        cond_copy_kernel<<<nb, 256, 0, st>>>(out_dev, (const double2*)ch->noise_new[k], (double2*)ch->noise_cur[k], N);
+        if (k >= 1)
+            cond_copy_kernel<<<148 * 8, 256, 0, st>>>(out_dev, (const double2*)ch->L_latest[k], (double2*)ch->L_cur[k],
+                                                      size_t(N) * ch->ldl);
+    }
+    cond_copy_scalar_kernel<<<1, 32, 0, st>>>(out_dev, phi_new3, phi_cur3, 3);   // keeps a cached Phi(current) in step
+    MSPDE_LAUNCH_CHECK();
+    // Gibbs part: uses noise_cur after the accept copy and L_latest even after a rejection (Appendix A.4-3)
+    propose_kernel<<<nb, 256, 0, st>>>((const cplx*)ch->noise_cur[K - 1], (const cplx*)nz->w_last, ch->beta, ch->betaZ, N,
+                                       nr, (cplx*)ch->noise_new[K - 1], nullptr, nullptr);
+    MSPDE_LAUNCH_CHECK();
+    if (!(flags & MSPDE_STEP_SKIP_GIBBS)) {
+        rc = copy2d(st, c->QRaug, c->ldA, c->H, c->ldH, M, N);
+        if (rc) return rc;
+        rc = copy2d(st, c->QRaug + size_t(M) * c->ldA, c->ldA, (const cplx*)ch->L_latest[K - 1], ch->ldl, N, N);
+        if (rc) return rc;
+        gibbs_rhs_kernel<<<(M + N + 255) / 256, 256, 0, st>>>(c->QRaug, c->ldA, N, c->y, nz->e, (const cplx*)ch->noise_new[K - 1], M, N);
+        MSPDE_LAUNCH_CHECK();
+        rc = lstsq_qr_aug(st, c->QRaug, c->ldA, M + N, N, c->qr_work, (cplx*)ch->u_new[K - 1], nullptr);
+        if (rc) return rc;
+    }
+    if (record_dev) {
+        for (int k = 0; k < K; ++k) {
+            record_kernel<<<(nr + 255) / 256, 256, 0, st>>>((const cplx*)ch->u_cur[k], nr, record_dev + size_t(k) * nr);
+        }
+        MSPDE_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace mspde

@@ -13,6 +13,32 @@ from . import _ffi
 c_double = ctypes.c_double
 CDTYPE = torch.complex128
 
+STEP_CACHE_PHI_CUR = 1
+STEP_SKIP_GIBBS = 2
+
+
+class _Chain(ctypes.Structure):
+    """mspde_chain of include/mspde.h."""
+    _fields_ = [("n_layers", ctypes.c_int), ("beta", c_double), ("betaZ", c_double),
+                ("sqrt_betas", ctypes.POINTER(c_double)),
+                ("noise_cur", ctypes.POINTER(ctypes.c_void_p)), ("noise_new", ctypes.POINTER(ctypes.c_void_p)),
+                ("u_cur", ctypes.POINTER(ctypes.c_void_p)), ("u_new", ctypes.POINTER(ctypes.c_void_p)),
+                ("L_cur", ctypes.POINTER(ctypes.c_void_p)), ("L_latest", ctypes.POINTER(ctypes.c_void_p)),
+                ("ldl", ctypes.c_int), ("phi_cur_valid", ctypes.c_int)]
+
+
+class _StepNoise(ctypes.Structure):
+    """mspde_step_noise of include/mspde.h."""
+    _fields_ = [("w_half", ctypes.POINTER(ctypes.c_void_p)), ("w_last", ctypes.c_void_p),
+                ("e", ctypes.c_void_p), ("log_u", c_double)]
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
 
 def _round_up(x, a):
     return (x + a - 1) // a * a
@@ -107,6 +133,43 @@ class MspdeContext:
         v = self.scal[:3].cpu().numpy()
         return (float(v[0]), float(v[1]), float(v[2])) if parts else float(v[0])
 
+    def solve(self, L, rhs, want_logdet: bool = False):
+        """x = L^-1 rhs (cp.linalg.solve call sites); optionally also log|det L| (Lmatrix_2D.logDet)."""
+        self._sync_stream()
+        x = torch.empty(self.N, dtype=CDTYPE, device=self.device)
+        ld = self.scal[8:9]
+        _ffi.check(self.lib.mspde_solve(self._h, _ffi.ptr(L), L.stride(0), _ffi.ptr(rhs), _ffi.ptr(x), _ffi.ptr(ld)), "solve")
+        return (x, float(ld.item())) if want_logdet else x
+
+    def lstsq(self, a, b):
+        """util.lstsq(a, b)[0] for a (rows x cols) with unit column stride."""
+        self._sync_stream()
+        rows, cols = a.shape
+        if a.stride(1) != 1:
+            a = a.contiguous()
+        x = torch.empty(cols, dtype=CDTYPE, device=self.device)
+        _ffi.check(self.lib.mspde_lstsq(self._h, _ffi.ptr(a), a.stride(0), rows, cols, _ffi.ptr(b), _ffi.ptr(x)), "lstsq")
+        return x
+
+    def gibbs_lstsq(self, L, rhs):
+        self._sync_stream()
+        v = torch.empty(self.N, dtype=CDTYPE, device=self.device)
+        _ffi.check(self.lib.mspde_gibbs_lstsq(self._h, _ffi.ptr(L), L.stride(0), _ffi.ptr(rhs), _ffi.ptr(v)), "gibbs_lstsq")
+        return v
+
+    def pcn_step(self, chain: "ChainBuffers", w_half, log_u: float, w_last, e, flags: int = 0, record=None, out=None):
+        """One pCN.one_step on the device.  Returns the 4-double device tensor {accepted, logRatio, Phi_cur, Phi_new}."""
+        self._sync_stream()
+        K = self.n_layers
+        out = torch.empty(4, dtype=torch.float64, device=self.device) if out is None else out
+        cs = chain.as_struct()
+        wh = _ptr_array(list(w_half))
+        nz = _StepNoise(ctypes.cast(wh, ctypes.POINTER(ctypes.c_void_p)), w_last.data_ptr(), e.data_ptr(), float(log_u))
+        _ffi.check(self.lib.mspde_pcn_step(self._h, ctypes.byref(cs), ctypes.byref(nz), int(flags), _ffi.ptr(out),
+                                           _ffi.ptr(record)), "pcn_step")
+        chain.phi_cur_valid = 1
+        return out
+
     def check_info(self, what: str):
         info = self.lib.mspde_read_info(self._h, 1)
         _ffi.check(info, what)
@@ -131,3 +194,35 @@ def _view_from_ptr(p: int, rows: int, cols: int, ld: int, device) -> torch.Tenso
     raw.__cuda_array_interface__ = {"shape": (rows * ld * 2,), "typestr": "<f8", "data": (int(p), False), "version": 2}
     flat = torch.as_tensor(raw, device=device)
     return torch.view_as_complex(flat.view(rows, ld, 2))[:, :cols]
+
+
+class ChainBuffers:
+    """Device-resident state of one chain: per layer noise_cur/new, u_cur/new (N complex)
+    and, for layers k >= 1, L_cur / L_latest (N x ldN)."""
+
+    def __init__(self, ctx: MspdeContext, sqrt_betas, beta: float = 1.0):
+        K, N = ctx.n_layers, ctx.N
+        self.ctx = ctx
+        z = lambda: torch.zeros(N, dtype=CDTYPE, device=ctx.device)
+        self.noise_cur = [z() for _ in range(K)]
+        self.noise_new = [z() for _ in range(K)]
+        self.u_cur = [z() for _ in range(K)]
+        self.u_new = [z() for _ in range(K)]
+        self.L_cur = [None] + [ctx.new_matrix(N, N) for _ in range(K - 1)]
+        self.L_latest = [None] + [ctx.new_matrix(N, N) for _ in range(K - 1)]
+        self.sqrt_betas = [float(s) for s in sqrt_betas]
+        self._sb = (c_double * K)(*self.sqrt_betas)
+        self.phi_cur_valid = 0
+        self.set_step(beta)
+
+    def set_step(self, beta: float):
+        self.beta = float(beta)
+        self.betaZ = float(np.sqrt(max(0.0, 1.0 - self.beta ** 2)))
+
+    def as_struct(self) -> _Chain:
+        K = self.ctx.n_layers
+        self._arrs = [_ptr_array(x) for x in (self.noise_cur, self.noise_new, self.u_cur, self.u_new, self.L_cur,
+                                              self.L_latest)]
+        casted = [ctypes.cast(a, ctypes.POINTER(ctypes.c_void_p)) for a in self._arrs]
+        return _Chain(K, self.beta, self.betaZ, ctypes.cast(self._sb, ctypes.POINTER(c_double)), *casted,
+                      self.L_cur[1].stride(0), self.phi_cur_valid)
