@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- pCN iterations/s of the B200-native hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # ours (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the numpy oracle port on the host cores
+
+Workload (config.workload): BASELINE.json configs[1] -- 2-D Shepp-Logan tomography, 3 layers, n=32 Fourier
+modes/axis (N=3969), n_ext=64 (m=127), 90 angles (M=11430), single chain per GPU; synthetic sinogram.
+A "step" is one pCN.one_step (reference-faithful formulation: Phi(current) recomputed every iteration).
+  value : iterations/s with the injected noise already resident in HBM (device-timed, CUDA events)
+  e2e   : iterations/s through the public API pCN.one_step(Layers, noise=...) with the step's noise copied from
+          pinned host memory and the accept flag + recorded samples read back every step
+For N>1 the chains are independent (one per rank, different seeds): no data-path collective, one final NCCL
+all_gather of the recorded samples inside the timed region; scaling is weak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "mcmc-multispde_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+CONFIGS = {
+    1: dict(n=16, n_ext=64, n_theta=45, n_layers=2),
+    2: dict(n=32, n_ext=64, n_theta=90, n_layers=3),
+    3: dict(n=64, n_ext=64, n_theta=90, n_layers=3),
+}
+FP64_PEAK_TFLOPS = 37.15   # measured on this pool's B200: DMMA m8n8k4 microbenchmark, profiles/r01_fp64_probe.log
+
+
+def flops_iter(n, n_ext, n_theta, n_layers):
+    """F_iter = (layers-2)*8/3 N^3 + 2 F_Phi + F_QR (real flops, structure-exploiting count)."""
+    N = (2 * n - 1) ** 2
+    M = (2 * n_ext - 1) * n_theta
+    f_phi = 4 * N ** 3 + 4 / 3 * N ** 3 + 4 * N * N * M + 4 * M * M * N + 4 / 3 * M ** 3
+    f_qr = 8 * (M + N) * N * N - 8 / 3 * N ** 3
+    return (n_layers - 2) * 8 / 3 * N ** 3 + 2 * f_phi + f_qr, N, M
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the numpy oracle (port of the reference step) on the host cores, on a bounded sample
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=30.0):
+    """Times the oracle's one_step on the largest geometry that fits the budget and scales to `cfg` by flop ratio.
+    Returns (iters_per_s_at_cfg, description, cores)."""
+    from oracle import mspde_oracle as o
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    a = (np.random.rand(1500, 1500) + 1j * np.random.rand(1500, 1500))
+    t0 = time.perf_counter(); a @ a; t1 = time.perf_counter()
+    gfs = 8 * 1500 ** 3 / (t1 - t0)
+    f_target, _, _ = flops_iter(**cfg)
+    cands = [(cfg["n"], cfg["n_theta"]), (24, 60), (16, 45), (12, 30), (8, 24)]
+    chosen = cands[-1]
+    for n, nth in cands:
+        if n > cfg["n"]:
+            continue
+        f, _, _ = flops_iter(n, cfg["n_ext"], nth, cfg["n_layers"])
+        if 2.2 * f / gfs * (steps + warmup + 1) <= budget_s * max(1, steps):   # numpy does ~2.2x the structured count
+            chosen = (n, nth)
+            break
+    n, nth = chosen
+    hp = o.Hyper(n_layers=cfg["n_layers"], n=n, n_ext=cfg["n_ext"], n_theta=nth)
+    pb = o.synthetic_problem(hp)
+    ft, H, HtH, y, delta = pb["ft"], pb["H"], pb["HtH"], pb["y"], pb["delta"]
+    ns = o.NoiseStream(11, hp.n_layers, ft.n_ravel, H.shape[0])
+    K = hp.n_layers
+    st = o.init_chain(hp, ft, [ns.half() for _ in range(K)], [ns.half() for _ in range(K)])
+    for _ in range(warmup):
+        o.one_step(st, ft, H, HtH, y, delta, ns.draw_iteration())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.one_step(st, ft, H, HtH, y, delta, ns.draw_iteration())
+    dt = (time.perf_counter() - t0) / steps
+    f_sample, _, _ = flops_iter(n, cfg["n_ext"], nth, cfg["n_layers"])
+    rate = (1.0 / dt) * (f_sample / f_target)
+    desc = (f"{steps} full oracle iteration(s) at n={n}, {nth} angles, {cfg['n_layers']} layers ({dt:.2f} s each, numpy/OpenBLAS "
+            f"{cores} threads)" + ("" if (n, nth) == (cfg["n"], cfg["n_theta"]) else
+                                   f", scaled to the workload by the F_iter ratio {f_sample / f_target:.4f}"))
+    return rate, desc, cores, dt
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    rate, desc, cores, dt = cpu_oracle_rate(cfg, steps=max(1, args.steps), warmup=min(args.warmup, 1), budget_s=25.0)
+    line = {"impl": "reference", "metric": "pCN iters/sec (n=32, 3 layers)", "value": rate, "unit": "iters/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / rate,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(cfg, args.gpus),
+            "cpu_baseline": {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": rate, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(cfg, gpus):
+    return {"workload": f"BASELINE configs[1]: Shepp-Logan tomography, {cfg['n_layers']} layers, n={cfg['n']} modes/axis, "
+                        f"n_ext={cfg['n_ext']}, {cfg['n_theta']} angles, one chain per GPU",
+            "formulation": "reference-faithful (Phi(current) recomputed every step, Gibbs QR every step)",
+            "cache": "working set per step (L 252 MB, Q_inv 2.1 GB, H 726 MB) >> 126 MB L2; no explicit flush",
+            "parallelism": f"{gpus} independent chain(s), no data-path collective; final NCCL all_gather of samples"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cache-phi", action="store_true", help="also report the results-preserving cached-Phi(current) rate")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mspde import image as im
+    from mspde import util, _ffi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    f_iter, N, M = flops_iter(**cfg)
+    K = cfg["n_layers"]
+    t_setup = time.perf_counter()
+    sim = im.Simulation(n_layers=K, n_samples=args.steps * 2 + args.warmup * 2 + 8, n=cfg["n"], n_extended=cfg["n_ext"], beta=0.3,
+                        kappa=5e9, sigma_0=4e7, sigma_v=3.2e4, sigma_scaling=0.4, meas_std=0.2, evaluation_interval=10,
+                        printProgress=False, seed=1 + rank, burn_percentage=25.0, enable_step_adaptation=True,
+                        pcn_variant="dunlop", phantom_name="shepp.png", meas_type="tomo", n_theta=cfg["n_theta"],
+                        verbose=False, device=local_rank)
+    sim.pcn.set_chol_epsilon(1e-6)
+    pcn, ctx, Layers = sim.pcn, sim.pcn.ctx, sim.Layers
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    nr = sim.fourier.basis_number_2D_ravel
+
+    # ---- injected noise for every step, generated once on the host (pinned) in the reference's RNG call order
+    rng = np.random.Generator(np.random.PCG64(1000 + rank))
+    total = 2 * (args.warmup + args.steps)
+
+    def host_noise():
+        w = [util.w_half_from_normals(rng.standard_normal(nr), rng.standard_normal(nr)) for _ in range(K - 1)]
+        log_u = float(np.log(rng.random()))
+        w_last = util.w_half_from_normals(rng.standard_normal(nr), rng.standard_normal(nr))
+        e = rng.standard_normal(M)
+        return ([torch.from_numpy(x).pin_memory() for x in w], log_u, torch.from_numpy(w_last).pin_memory(),
+                torch.from_numpy(e).pin_memory())
+    noises = [host_noise() for _ in range(total)]
+    h2d_bytes = sum(x.numel() * x.element_size() for x in noises[0][0]) + noises[0][2].numel() * 16 + noises[0][3].numel() * 8
+    d2h_bytes = 4 * 8 + K * nr * 16
+
+    def to_dev(nz):
+        return [x.to(dev, non_blocking=True) for x in nz[0]], nz[1], nz[2].to(dev, non_blocking=True), nz[3].to(dev, non_blocking=True)
+
+    lib = _ffi.lib()
+    lib.mspde_launch_count.restype = __import__("ctypes").c_longlong
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- arm 1: device-resident inputs, no host sync inside the loop -------------------------------------------
+    pcn._ensure_inputs(Layers[0].stdev_sym_host)
+    cb = pcn._bind(Layers)
+    dev_noise = [to_dev(nz) for nz in noises[:args.warmup + args.steps]]
+    rec = torch.zeros((args.steps + args.warmup, K, nr), dtype=torch.complex128, device=dev)
+    outs = torch.zeros((args.steps + args.warmup, 4), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    for i in range(args.warmup):
+        w, lu, wl, e = dev_noise[i]
+        ctx.pcn_step(cb, w, lu, wl, e, record=rec[i], out=outs[i])
+    ctx.check_info("warm-up")
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.mspde_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.warmup, args.warmup + args.steps):
+        w, lu, wl, e = dev_noise[i]
+        ctx.pcn_step(cb, w, lu, wl, e, record=rec[i], out=outs[i])
+    if world > 1:
+        gathered = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(gathered, rec)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.mspde_launch_count() - launches0
+    ctx.check_info("timed region")
+    ms_dev = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev = float(t.item())
+    value = world * args.steps / (ms_dev * 1e-3)
+    acc_rate = float(outs[args.warmup:, 0].mean().item())
+
+    # ---- arm 2: end to end through the public API, host noise in pinned memory, results read back every step ----
+    base = args.warmup + args.steps
+    for i in range(min(args.warmup, 2)):
+        pcn.one_step(Layers, noise=to_dev(noises[base + i]))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.warmup, args.warmup + args.steps):
+        pcn.one_step(Layers, noise=to_dev(noises[base + i]))
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_e2e = float(t.item())
+    e2e_value = world * args.steps / t_e2e
+
+    extra = {}
+    if args.cache_phi:
+        pcn.cache_phi_current = True
+        pcn.one_step(Layers, noise=to_dev(noises[0]))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            pcn.one_step(Layers, noise=to_dev(noises[1 + i]))
+        torch.cuda.synchronize()
+        extra["e2e_cached_phi_current"] = {"value": world * args.steps / (time.perf_counter() - t0), "unit": "iters/s",
+                                           "note": "results-preserving: Phi(L_cur) reused until the next acceptance"}
+        pcn.cache_phi_current = False
+
+    # ---- roofline of the dominant kernel: zgemm_tn_kernel on its largest launch, Q_inv = I - Ht^H Ht (upper) ----
+    roofline = None
+    if rank == 0:
+        X = ctx.buffer("X", N, M)
+        Q = ctx.buffer("Q", M, M)
+        reps = 3
+        ctx.gemm_tn(X, X, conjA=True, alpha=-1.0, beta=0.0, C=Q, upper=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ctx.gemm_tn(X, X, conjA=True, alpha=-1.0, beta=0.0, C=Q, upper=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_k = e0.elapsed_time(e1) / reps
+        fl = 4.0 * M * M * N          # ZHERK m x m x k = 4 m^2 k real flops
+        ach = fl / (ms_k * 1e-3) / 1e12
+        roofline = {"kernel": "zgemm_tn_kernel (DMMA m8n8k4), launch Q_inv = I - Ht^H Ht, upper triangle, m=n=%d k=%d" % (M, N),
+                    "bound": "tensor", "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
+                    "traffic": None, "ms_per_launch": ms_k,
+                    "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_fp64_probe.log); "
+                                   "MEASURED_PEAKS.json has no FP64 entry",
+                    "step_fp64": {"flops_per_step": f_iter, "achieved": f_iter / (ms_dev * 1e-3 / args.steps) / 1e12,
+                                  "frac": f_iter / (ms_dev * 1e-3 / args.steps) / 1e12 / FP64_PEAK_TFLOPS}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, desc, cores, dt = cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=25.0)
+        cpu_baseline = {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        line = {"metric": "pCN iters/sec (n=32, 3 layers)", "value": value, "unit": "iters/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(cfg, world),
+                "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "acceptance_rate": acc_rate, "setup_s": t_setup}
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

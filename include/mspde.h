@@ -21,6 +21,7 @@ extern "C" {
 typedef struct mspde_ctx mspde_ctx;
 
 const char* mspde_last_error(void);
+long long mspde_launch_count(void);   /* kernels launched by the library so far (bench.py gpu_launches) */
 
 /* Context = sizes + borrowed fixed inputs + library-owned workspace (replaces the managed-memory pool and the
  * temporaries of pCN._log_ratio, mcmc/image_cupy.py:834-835, 634-643). */

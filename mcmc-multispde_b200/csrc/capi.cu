@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+long long g_launches = 0;
 
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
@@ -40,6 +41,7 @@ struct mspde_ctx {
 extern "C" {
 
 const char* mspde_last_error(void) { return get_error(); }
+long long mspde_launch_count(void) { return g_launches; }
 
 int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n_layers, void* stream) {
     if (!out || n < 2 || n_ext < n || M < 1 || n_layers < 2) {

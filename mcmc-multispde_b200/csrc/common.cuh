@@ -11,6 +11,7 @@ namespace mspde {
 
 void set_error(const char* fmt, ...);
 const char* get_error();
+extern long long g_launches;   // kernels launched by this library (bench.py reports it as gpu_launches)
 
 #define MSPDE_CUDA(expr)                                                                      \
     do {                                                                                      \
@@ -24,6 +25,7 @@ const char* get_error();
 
 #define MSPDE_LAUNCH_CHECK()                                                                  \
     do {                                                                                      \
+        ++mspde::g_launches;                                                                  \
         cudaError_t e__ = cudaGetLastError();                                                 \
         if (e__ != cudaSuccess) {                                                             \
             mspde::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,         \

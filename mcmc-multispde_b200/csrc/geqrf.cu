@@ -294,6 +294,7 @@ int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, v
         double* la = logabs;
         void* args[] = {&Ap, &lda_, &mp_, &pw_, &slab_, &V, &Vt, &ldvt, &tau, &dots, &currow, &la};
         MSPDE_CUDA(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(G), dim3(256), args, smem, st));
+        ++g_launches;
         const int n2 = ntot - (c0 + pw);
         if (n2 <= 0) continue;
         // T from V^H V

@@ -75,7 +75,7 @@ class MspdeContext:
 
     # ---- inputs ---------------------------------------------------------------------------------------
     def to_dev(self, a, dtype=None):
-        t = torch.as_tensor(np.ascontiguousarray(a))
+        t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(a))
         if dtype is not None:
             t = t.to(dtype)
         return t.to(self.device)
@@ -99,6 +99,29 @@ class MspdeContext:
         _ffi.check(self.lib.mspde_ctx_set_inputs(self._h, _ffi.ptr(Hd), Hd.stride(0), _ffi.ptr(Hct), Hct.stride(0),
                                                  _ffi.ptr(HtHd), HtHd.stride(0), _ffi.ptr(yd), _ffi.ptr(Dd), _ffi.ptr(sd),
                                                  c_double(float(delta))), "mspde_ctx_set_inputs")
+
+    def update_scalars(self, stdev_sym=None, delta=None):
+        """Re-register the inputs after a change of the diagonal prior or the Cholesky stabiliser (no matrix copies)."""
+        if stdev_sym is not None:
+            self.stdev_sym = self.to_dev(stdev_sym, torch.float64)
+            self._keep["stdev"] = self.stdev_sym
+        if delta is not None:
+            self.delta = float(delta)
+        _ffi.check(self.lib.mspde_ctx_set_inputs(self._h, _ffi.ptr(self.H), self.H.stride(0), _ffi.ptr(self.Hct),
+                                                 self.Hct.stride(0), _ffi.ptr(self.HtH), self.HtH.stride(0), _ffi.ptr(self.y),
+                                                 _ffi.ptr(self.D_diag), _ffi.ptr(self.stdev_sym), c_double(self.delta)),
+                   "mspde_ctx_set_inputs")
+
+    def gemm_tn(self, A, B, conjA=True, alpha=1.0, beta=0.0, C=None, upper=False):
+        """C = alpha * op(A)^T B + beta * C with A (k x m), B (k x n) row-major (mspde_zgemm_tn)."""
+        k, m = A.shape
+        n = B.shape[1]
+        if C is None:
+            C = self.new_matrix(m, n)
+        _ffi.check(self.lib.mspde_zgemm_tn(_ffi.current_stream(), int(conjA), m, n, k, c_double(alpha), _ffi.ptr(A),
+                                           A.stride(0), _ffi.ptr(B), B.stride(0), c_double(beta), _ffi.ptr(C), C.stride(0),
+                                           1 if upper else 0, None, 1), "zgemm_tn")
+        return C
 
     def _sync_stream(self):
         _ffi.check(self.lib.mspde_ctx_set_stream(self._h, _ffi.current_stream()), "set_stream")
