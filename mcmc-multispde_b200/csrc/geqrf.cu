@@ -234,7 +234,7 @@ QrWork carve(void* work, int rows, int cols) {
     w.V = (cplx*)take(size_t(rows) * PW * sizeof(cplx));
     w.Vt = (cplx*)take(size_t(PW) * w.ldvt * sizeof(cplx));
     w.W = (cplx*)take(size_t(PW) * w.ldw * sizeof(cplx));
-    w.part = (cplx*)take(size_t(w.nsplit + 1) * PW * w.ldw * sizeof(cplx));
+    w.part = (cplx*)take(size_t(w.nsplit + 1) * PW * size_t(w.ldw > PW ? w.ldw : PW) * sizeof(cplx));
     w.Gm = (cplx*)take(size_t(PW) * PW * sizeof(cplx));
     w.T = (cplx*)take(size_t(PW) * PW * sizeof(cplx));
     w.tau = (cplx*)take(size_t(PW) * sizeof(cplx));
@@ -253,7 +253,7 @@ size_t qr_work_bytes(int rows, int cols) {
     b += align_up(size_t(rows) * PW * sizeof(cplx));
     b += align_up(size_t(PW) * ldvt * sizeof(cplx));
     b += align_up(size_t(PW) * ldw * sizeof(cplx));
-    b += align_up(size_t(7) * PW * ldw * sizeof(cplx));
+    b += align_up(size_t(7) * PW * (ldw > PW ? ldw : PW) * sizeof(cplx));
     b += 3 * align_up(size_t(PW) * PW * sizeof(cplx));
     b += align_up(size_t(2) * MAXG * PW * sizeof(cplx));
     b += align_up(size_t(2) * PW * sizeof(cplx));

@@ -1,0 +1,359 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the numpy oracle on the same seeded
+inputs (small sizes), against the committed goldens, and -- at BASELINE config-2 size -- through size-independent
+properties and a torch.linalg (cuBLAS/cuSOLVER) rendition used only as a checker.
+
+Tolerances: index/byte work bit-exact; FP64 results 1e-10 relative (BASELINE.json north_star)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mspde_oracle as o
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mspde import _ffi
+    return _ffi.lib()
+
+
+def _gemm(lib, A, B, C, conj=True, alpha=1.0, beta=0.0, uplo=0, ws=None, nsplit=1):
+    from mspde import _ffi
+    k, m = A.shape
+    n = B.shape[1]
+    _ffi.check(lib.mspde_zgemm_tn(_ffi.current_stream(), int(conj), m, n, k, ctypes.c_double(alpha), _ffi.ptr(A), A.stride(0),
+                                  _ffi.ptr(B), B.stride(0), ctypes.c_double(beta), _ffi.ptr(C), C.stride(0), uplo, _ffi.ptr(ws),
+                                  nsplit), "zgemm_tn")
+
+
+def crandn(*shape, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.complex(torch.randn(*shape, dtype=torch.float64, device="cuda", generator=g),
+                         torch.randn(*shape, dtype=torch.float64, device="cuda", generator=g))
+
+
+# ------------------------------------------------------------------------------------------------ building blocks
+@pytest.mark.parametrize("m,n,k,conj,uplo,beta", [(64, 64, 16, 1, 0, 0.0), (1, 1, 1, 1, 0, 0.0), (100, 77, 35, 0, 0, 0.0),
+                                                 (200, 130, 129, 1, 0, 1.0), (333, 333, 211, 1, 1, 1.0), (49, 1016, 49, 1, 0, -1.0),
+                                                 (961, 961, 961, 1, 1, 0.0), (65, 63, 1, 1, 0, 0.0)])
+def test_zgemm_tn_matches_cublas(lib, m, n, k, conj, uplo, beta):
+    A = crandn(k, m, seed=1)
+    B = A if uplo else crandn(k, n, seed=2)
+    C = crandn(m, n, seed=3)
+    C0 = C.clone()
+    alpha = -1.0 if beta else 1.0
+    ref = alpha * ((A.conj().T if conj else A.T) @ B) + beta * C0
+    _gemm(lib, A, B, C, conj, alpha, beta, uplo)
+    torch.cuda.synchronize()
+    if uplo:
+        mask = torch.triu(torch.ones(m, n, dtype=torch.bool, device="cuda"))
+        assert torch.equal(C[~mask], C0[~mask])                      # strictly-lower part untouched
+        assert rel(C[mask].cpu(), ref[mask].cpu()) < 1e-13
+    else:
+        assert rel(C.cpu(), ref.cpu()) < 1e-13
+
+
+def test_zgemm_tn_splitk_deterministic(lib):
+    A, B = crandn(3001, 64, seed=4), crandn(3001, 500, seed=5)
+    ws = torch.empty(8 * 64 * 500, dtype=torch.complex128, device="cuda")
+    C1 = torch.zeros(64, 500, dtype=torch.complex128, device="cuda")
+    C2 = torch.zeros_like(C1)
+    _gemm(lib, A, B, C1, ws=ws, nsplit=8)
+    _gemm(lib, A, B, C2, ws=ws, nsplit=8)
+    torch.cuda.synchronize()
+    assert torch.equal(C1, C2)
+    assert rel(C1.cpu(), (A.conj().T @ B).cpu()) < 1e-13
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 65, 200, 777])
+def test_potrf_and_trsm(lib, n):
+    from mspde import _ffi
+    A = crandn(n + 3, n, seed=n)
+    Hm = A.conj().T @ A + n * torch.eye(n, dtype=torch.complex128, device="cuda")
+    Uref = torch.linalg.cholesky(Hm).conj().T
+    W = torch.triu(Hm).contiguous()
+    winv = torch.zeros(((n + 63) // 64) * 64 * 64, dtype=torch.complex128, device="cuda")
+    info = torch.zeros(4, dtype=torch.int32, device="cuda")
+    st = _ffi.current_stream()
+    _ffi.check(lib.mspde_zpotrf_upper(st, _ffi.ptr(W), W.stride(0), n, _ffi.ptr(winv), _ffi.ptr(info)))
+    torch.cuda.synchronize()
+    assert int(info[0]) == 0
+    assert rel(torch.triu(W).cpu(), Uref.cpu()) < 1e-12
+    B = crandn(n, 37, seed=n + 1)
+    X = B.clone()
+    _ffi.check(lib.mspde_ztrsm_uh(st, _ffi.ptr(W), W.stride(0), _ffi.ptr(winv), n, _ffi.ptr(X), X.stride(0), 37))
+    torch.cuda.synchronize()
+    ref = torch.linalg.solve_triangular(Uref.conj().T, B, upper=False)
+    assert rel(X.cpu(), ref.cpu()) < 1e-11
+
+
+def test_potrf_reports_not_positive_definite(lib):
+    from mspde import _ffi
+    n = 130
+    Hm = torch.eye(n, dtype=torch.complex128, device="cuda")
+    Hm[70, 70] = -1.0
+    winv = torch.zeros(3 * 64 * 64, dtype=torch.complex128, device="cuda")
+    info = torch.zeros(4, dtype=torch.int32, device="cuda")
+    _ffi.check(lib.mspde_zpotrf_upper(_ffi.current_stream(), _ffi.ptr(Hm), Hm.stride(0), n, _ffi.ptr(winv), _ffi.ptr(info)))
+    torch.cuda.synchronize()
+    assert int(info[0]) == 71                                        # LAPACK zpotrf info convention (1-based)
+    with pytest.raises(np.linalg.LinAlgError):
+        _ffi.check(int(info[0]), "zpotrf")
+
+
+# ------------------------------------------------------------------------------------------------ assembly
+@pytest.fixture(scope="module")
+def toy():
+    from mspde.core import MspdeContext
+    hp = o.Hyper(n_layers=3, n=4, n_ext=64, n_theta=8)
+    pb = o.synthetic_problem(hp)
+    pt = o.prior_tables(hp, pb["ft"])
+    ns = o.NoiseStream(7, 3, pb["ft"].n_ravel, pb["H"].shape[0])
+    st = o.init_chain(hp, pb["ft"], [ns.half() for _ in range(3)], [ns.half() for _ in range(3)])
+    ctx = MspdeContext(4, 64, pb["H"].shape[0], 3)
+    ctx.set_inputs(pb["H"], pb["HtH"], pb["y"], pb["ft"].D_diag, pt["stdev_sym"], pb["delta"])
+    return hp, pb, pt, ns, st, ctx
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_assembly_kernel_index_map_bit_exact_vs_reference_kernel(golden_dir, n):
+    """Label every table entry, run the CUDA assembly with D = 1, Tm = 0, sqrt_beta = 1: the output must equal the
+    reference's own _construct_U output (golden, produced by the reference kernel body) bit for bit."""
+    from mspde.core import MspdeContext
+    g = np.load(os.path.join(golden_dir, f"ref_construct_U_n{n}.npz"))
+    ctx = MspdeContext(n, 8, 16, 2)
+    N = ctx.N
+    ones = np.ones(N)
+    z = np.zeros((4, N), dtype=np.complex128)
+    ctx.set_inputs(np.zeros((16, N), np.complex128), np.zeros((N, N), np.complex128), np.zeros(16), ones, ones, 0.0)
+    tp = ctx.to_dev(g["labels"].astype(np.complex128))
+    tm = torch.zeros_like(tp)
+    L = ctx.assemble_L(tp, tm, 1.0).cpu().numpy()
+    assert np.array_equal(L.real.astype(np.int32), g["U"]) and not L.imag.any()
+
+
+def test_field_coeffs_and_L_vs_oracle(toy):
+    hp, pb, pt, ns, st, ctx = toy
+    ft = pb["ft"]
+    for k in (1, 2):
+        u, sb = st.u_cur_sym[k - 1], st.sqrt_betas[k]
+        tp, tm = o.field_coeffs(u, ft)
+        tpd, tmd = ctx.field_coeffs(ctx.to_dev(u))
+        assert rel(tpd.cpu(), tp) < RTOL and rel(tmd.cpu(), tm) < RTOL
+        Lo = o.assemble_L_from_tables(tp, tm, ft.D_diag, sb)
+        Ld = ctx.assemble_L(ctx.to_dev(tp), ctx.to_dev(tm), sb).cpu().numpy()
+        assert np.array_equal(Ld, Lo)                                # same tables -> bit-identical Galerkin matrix
+        Le = ctx.construct_L(ctx.to_dev(u), sb).cpu().numpy()
+        assert rel(Le, st.L_cur[k]) < RTOL
+
+
+def test_phi_solve_lstsq_vs_oracle(toy):
+    hp, pb, pt, ns, st, ctx = toy
+    ft, H, HtH, y, delta = pb["ft"], pb["H"], pb["HtH"], pb["y"], pb["delta"]
+    N, M = ft.N, H.shape[0]
+    L = st.L_cur[2]
+    po, parts = o.phi_woodbury(L, H, HtH, y, delta, return_parts=True)
+    Ld = ctx.new_matrix(N, N); Ld.copy_(ctx.to_dev(L))
+    pg = ctx.phi(Ld, parts=True)
+    assert abs(pg[0] - po) <= RTOL * abs(po)
+    assert abs(pg[1] - parts["quad"]) <= RTOL * abs(parts["quad"]) and abs(pg[2] - parts["logdet"]) <= 1e-9 * abs(parts["logdet"])
+    assert rel(torch.triu(ctx.buffer("r", N, N)).cpu().numpy().conj().T, parts["c"]) < RTOL
+    assert rel(ctx.buffer("X", N, M).cpu(), parts["Ht"]) < RTOL
+    L1 = st.L_cur[1]
+    L1d = ctx.new_matrix(N, N); L1d.copy_(ctx.to_dev(L1))
+    x, ld = ctx.solve(L1d, ctx.to_dev(st.noise_cur[1]), want_logdet=True)
+    assert rel(x.cpu(), np.linalg.solve(L1, st.noise_cur[1])) < RTOL
+    assert abs(ld - o.logdet_L(L1)) <= RTOL * abs(o.logdet_L(L1))
+    rng = np.random.default_rng(0)
+    rhs = rng.standard_normal(M + N) + 1j * rng.standard_normal(M + N)
+    v = ctx.gibbs_lstsq(Ld, ctx.to_dev(rhs))
+    assert rel(v.cpu(), o.lstsq_qr(np.vstack((H, L)), rhs)) < RTOL
+    a = rng.standard_normal((300, 40)) + 1j * rng.standard_normal((300, 40))
+    b = rng.standard_normal(300) + 1j * rng.standard_normal(300)
+    xg = ctx.lstsq(ctx.to_dev(a), ctx.to_dev(b))
+    assert rel(xg.cpu(), o.lstsq_qr(a, b)) < RTOL
+
+
+def _load_chain(ctx, st):
+    from mspde.core import ChainBuffers
+    K = len(st.noise_cur)
+    cb = ChainBuffers(ctx, st.sqrt_betas, st.beta)
+    for k in range(K):
+        cb.noise_cur[k].copy_(ctx.to_dev(st.noise_cur[k])); cb.noise_new[k].copy_(ctx.to_dev(st.noise_new[k]))
+        cb.u_cur[k].copy_(ctx.to_dev(st.u_cur_sym[k])); cb.u_new[k].copy_(ctx.to_dev(st.u_new_sym[k]))
+        if k >= 1:
+            cb.L_cur[k].copy_(ctx.to_dev(st.L_cur[k])); cb.L_latest[k].copy_(ctx.to_dev(st.L_latest[k]))
+    return cb
+
+
+@pytest.mark.parametrize("n,n_theta,steps,cache", [(4, 8, 6, False), (4, 8, 6, True), (8, 24, 4, False), (3, 12, 5, False)])
+def test_pcn_chain_vs_oracle(n, n_theta, steps, cache):
+    """Whole iterations with injected noise: accept decisions identical, Phi / samples within 1e-10."""
+    from mspde.core import MspdeContext, STEP_CACHE_PHI_CUR
+    hp = o.Hyper(n_layers=3, n=n, n_ext=64, n_theta=n_theta)
+    pb = o.synthetic_problem(hp)
+    ft, H, HtH, y, delta = pb["ft"], pb["H"], pb["HtH"], pb["y"], pb["delta"]
+    pt = o.prior_tables(hp, ft)
+    K, M = 3, H.shape[0]
+    ns = o.NoiseStream(7, K, ft.n_ravel, M)
+    st = o.init_chain(hp, ft, [ns.half() for _ in range(K)], [ns.half() for _ in range(K)])
+    ctx = MspdeContext(n, 64, M, K)
+    ctx.set_inputs(H, HtH, y, ft.D_diag, pt["stdev_sym"], delta)
+    cb = _load_chain(ctx, st)
+    rec = torch.zeros((K, ft.n_ravel), dtype=torch.complex128, device=ctx.device)
+    min_margin = np.inf
+    for it in range(steps):
+        nz = ns.draw_iteration()
+        d = o.one_step(st, ft, H, HtH, y, delta, nz)
+        cb.set_step(st.beta)
+        out = ctx.pcn_step(cb, [ctx.to_dev(w) for w in nz["w_half"]], nz["log_u"], ctx.to_dev(nz["w_last"]), ctx.to_dev(nz["e"]),
+                           flags=STEP_CACHE_PHI_CUR if cache else 0, record=rec)
+        ctx.check_info("step")
+        g = out.cpu().numpy()
+        min_margin = min(min_margin, abs(d["log_ratio"] - d["log_u"]))
+        assert int(g[0]) == int(d["accepted"]), (it, g, d)
+        assert abs(g[2] - d["phi_cur"]) <= RTOL * abs(d["phi_cur"])
+        assert abs(g[3] - d["phi_new"]) <= RTOL * abs(d["phi_new"])
+        halves = o.current_halves(st, ft)
+        for k in range(K):
+            assert rel(rec[k].cpu(), halves[k]) < RTOL
+            assert rel(cb.u_new[k].cpu(), st.u_new_sym[k]) < RTOL
+            assert rel(cb.noise_cur[k].cpu(), st.noise_cur[k]) < 1e-14
+        if (it + 1) % 2 == 0:
+            o.adapt_step(st, hp)
+    assert min_margin > 1e-6      # no accept decision was a near-tie, so the identical decisions are meaningful
+
+
+def test_chain_against_committed_golden(golden_dir, toy):
+    """Same toy chain as tests/golden/oracle_chain_n4.npz (generated by oracle/make_golden.py in the build container)."""
+    hp, pb, pt, ns_unused, st_unused, ctx = toy
+    g = np.load(os.path.join(golden_dir, "oracle_chain_n4.npz"))
+    ft = pb["ft"]
+    ns = o.NoiseStream(7, 3, ft.n_ravel, pb["H"].shape[0])
+    st = o.init_chain(hp, ft, [ns.half() for _ in range(3)], [ns.half() for _ in range(3)])
+    cb = _load_chain(ctx, st)
+    rec = torch.zeros((3, ft.n_ravel), dtype=torch.complex128, device=ctx.device)
+    for it in range(6):
+        nz = ns.draw_iteration()
+        out = ctx.pcn_step(cb, [ctx.to_dev(w) for w in nz["w_half"]], nz["log_u"], ctx.to_dev(nz["w_last"]), ctx.to_dev(nz["e"]),
+                           record=rec).cpu().numpy()
+        assert int(out[0]) == int(g["accepted"][it])
+        assert abs(out[2] - g["phi_cur"][it]) <= RTOL * abs(g["phi_cur"][it])
+        assert abs(out[3] - g["phi_new"][it]) <= RTOL * abs(g["phi_new"][it])
+        assert rel(rec.cpu(), g["halves"][it]) < RTOL
+        assert rel(cb.u_new[2].cpu(), g["u_new_last"][it]) < RTOL
+
+
+# ------------------------------------------------------------------------------------------------ host mirror, full size
+def test_simulation_surface_small():
+    """The reference-facing classes run end to end and honour the reference's error behaviour."""
+    from mspde import image as im
+    sim = im.Simulation(n_layers=3, n_samples=6, n=4, n_extended=64, beta=0.5, kappa=5e9, sigma_0=4e7, sigma_v=3.2e4,
+                        sigma_scaling=0.4, meas_std=0.2, evaluation_interval=2, printProgress=False, seed=3, burn_percentage=25.0,
+                        enable_step_adaptation=True, pcn_variant="dunlop", phantom_name="shepp.png", n_theta=8)
+    sim.pcn.set_chol_epsilon(1e-6)
+    sim.run()
+    assert sim.Layers[0].i_record == 6 and np.isfinite(sim.Layers[2].samples_history).all()
+    assert 0.0 <= sim.acceptancePercentage <= 1.0
+    L = sim.Layers[2].LMat.current_L
+    assert abs(sim.pcn._log_ratio(L) - sim.pcn.last_step["phi_cur"]) >= 0.0     # callable on its own
+    # a non-positive-definite system must surface as numpy.linalg.LinAlgError (Simulation.run's only except clause)
+    sim.pcn.ctx.update_scalars(delta=-1e30)
+    with pytest.raises(np.linalg.LinAlgError):
+        sim.pcn._log_ratio(L)
+
+
+@pytest.fixture(scope="module")
+def full():
+    """BASELINE configs[1] geometry: n=32, n_ext=64, 90 angles, 3 layers (N=3969, M=11430)."""
+    from mspde import image as im
+    sim = im.Simulation(n_layers=3, n_samples=8, n=32, n_extended=64, beta=0.3, kappa=5e9, sigma_0=4e7, sigma_v=3.2e4,
+                        sigma_scaling=0.4, meas_std=0.2, evaluation_interval=10, printProgress=False, seed=1, burn_percentage=25.0,
+                        enable_step_adaptation=True, pcn_variant="dunlop", phantom_name="shepp.png", n_theta=90)
+    sim.pcn.set_chol_epsilon(1e-6)
+    sim.pcn._ensure_inputs(sim.Layers[0].stdev_sym_host)
+    return sim
+
+
+def test_full_size_constant_field_is_scaled_identity(full):
+    ctx = full.pcn.ctx
+    u = torch.zeros(ctx.N, dtype=torch.complex128, device=ctx.device)
+    L = ctx.construct_L(u, 2.0)
+    d = torch.diagonal(L).clone()
+    expect = ctx.m * (ctx.D_diag - 1.0) / 2.0
+    assert float((d.real - expect).abs().max()) <= 1e-9 * float(expect.abs().max())
+    L.diagonal().zero_()
+    assert float(L.abs().max()) <= 1e-9 * float(expect.abs().max())
+
+
+def test_full_size_phi_matches_cusolver_rendition(full):
+    """Phi at N=3969, M=11430 against a torch.linalg rendition of image_cupy.py:634-643 (checker only)."""
+    pcn, ctx = full.pcn, full.pcn.ctx
+    L = full.Layers[2].LMat.current_L
+    phi = ctx.phi(L, parts=True)
+    Lc = L.contiguous()
+    r = Lc.conj().T @ Lc + ctx.HtH + ctx.delta * torch.eye(ctx.N, dtype=torch.complex128, device=ctx.device)
+    c = torch.linalg.cholesky(r)
+    Ht = torch.linalg.solve_triangular(c, ctx.Hct.contiguous(), upper=False)
+    Qi = torch.eye(ctx.M, dtype=torch.complex128, device=ctx.device) - Ht.conj().T @ Ht
+    C = torch.linalg.cholesky(Qi)
+    quad = 0.5 * float(torch.linalg.norm(ctx.y.to(torch.complex128) @ C) ** 2)
+    logdet = float(torch.log(torch.diagonal(C).real).sum())
+    ref = quad - logdet
+    assert abs(phi[0] - ref) <= RTOL * abs(ref), (phi, ref)
+    assert abs(phi[1] - quad) <= RTOL * abs(quad) and abs(phi[2] - logdet) <= 1e-9 * abs(logdet)
+    U = torch.triu(ctx.buffer("r", ctx.N, ctx.N))
+    assert float((U.conj().T - c).abs().max()) <= 1e-9 * float(c.abs().max())
+
+
+def test_full_size_solve_and_lstsq_properties(full):
+    ctx = full.pcn.ctx
+    L = full.Layers[1].LMat.current_L
+    w = full.Layers[1].current_noise_sample
+    x, ld = ctx.solve(L, w, want_logdet=True)
+    Lc = L.contiguous()
+    resid = float(torch.linalg.norm(Lc @ x - w) / (torch.linalg.norm(Lc) * torch.linalg.norm(x)))
+    assert resid < 1e-14                                             # backward error of the dense solve
+    assert abs(ld - float(torch.linalg.slogdet(Lc)[1])) <= RTOL * abs(ld)
+    L2 = full.Layers[2].LMat.current_L
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rhs = torch.complex(torch.randn(ctx.M + ctx.N, dtype=torch.float64, device="cuda", generator=g),
+                        torch.randn(ctx.M + ctx.N, dtype=torch.float64, device="cuda", generator=g))
+    v = ctx.gibbs_lstsq(L2, rhs)
+    A = torch.cat((ctx.H.contiguous(), L2.contiguous()), 0)
+    grad = A.conj().T @ (A @ v - rhs)                                # normal-equation residual of the least-squares solution
+    assert float(torch.linalg.norm(grad)) <= 1e-11 * float(torch.linalg.norm(A) ** 2 * torch.linalg.norm(v))
+    vref = torch.linalg.lstsq(A, rhs.unsqueeze(1)).solution.squeeze(1)
+    assert float((v - vref).abs().max()) <= 1e-9 * float(vref.abs().max())
+
+
+def test_full_size_steps_are_reproducible(full):
+    """Two identical chains fed identical noise produce bit-identical results (deterministic reductions)."""
+    from mspde import util
+    pcn, ctx, Layers = full.pcn, full.pcn.ctx, full.Layers
+    rng = np.random.Generator(np.random.PCG64(3))
+    nr, M, K = ctx.n_ravel, ctx.M, 3
+    w = [ctx.to_dev(util.w_half_from_normals(rng.standard_normal(nr), rng.standard_normal(nr))) for _ in range(K - 1)]
+    wl = ctx.to_dev(util.w_half_from_normals(rng.standard_normal(nr), rng.standard_normal(nr)))
+    e = ctx.to_dev(rng.standard_normal(M))
+    snap = [(l._noise_cur.clone(), l._u_cur.clone()) for l in Layers]
+    res = []
+    for rep in range(2):
+        for l, (a, b) in zip(Layers, snap):
+            l._noise_cur.copy_(a); l._u_cur.copy_(b)
+        cb = pcn._bind(Layers)
+        out = ctx.pcn_step(cb, w, -0.3, wl, e).clone()
+        ctx.check_info("step")
+        res.append((out.cpu(), Layers[2]._u_new.clone().cpu(), Layers[1]._u_new.clone().cpu()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert torch.isfinite(res[0][1].abs()).all()

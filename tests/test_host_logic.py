@@ -1,0 +1,76 @@
+"""CPU tests of the host-side mirror: reshape/symmetrise helpers against the reference goldens, step adaptation,
+and the chain-parallel sharding + final gather over a 2-rank gloo group."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from mspde import parallel, util
+
+
+def test_util_helpers_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_util_helpers.npz"))
+    assert np.array_equal(util.symmetrize(g["half"]), g["sym"])
+    assert np.array_equal(util.symmetrize(torch.from_numpy(g["half"])).numpy(), g["sym"])
+    assert np.array_equal(util.symmetrize_2D(g["uh"]), g["sym2D"])
+    assert np.array_equal(util.symmetrize_2D(torch.from_numpy(g["uh"])).numpy(), g["sym2D"])
+    assert np.array_equal(util.extend2D(g["sym2D"], 6), g["ext2D"])
+    assert np.array_equal(util.extend2D(torch.from_numpy(g["sym2D"]), 6).numpy(), g["ext2D"])
+
+
+def test_ravel_reshape_conventions():
+    n = 3
+    il = 2 * n - 1
+    u = np.arange(il * il) + 0j
+    ref = u.reshape(il, il, order="F")[:, n - 1:]
+    assert np.array_equal(util.from_u_2D_ravel_to_uHalf_2D(u, n), ref)
+    assert np.array_equal(util.from_u_2D_ravel_to_uHalf_2D(torch.from_numpy(u), n).numpy(), ref)
+    a = np.arange(12).reshape(3, 4)
+    assert np.array_equal(util.ravel_F(torch.from_numpy(a)).numpy(), a.ravel("F"))
+
+
+def test_noise_half_vector():
+    from oracle import mspde_oracle as o
+    re, im = np.random.default_rng(0).standard_normal((2, 7))
+    assert np.array_equal(util.w_half_from_normals(re, im), o.w_half_from_normals(re, im))
+
+
+def test_sharding():
+    for world in (1, 2, 4, 8):
+        owned = [parallel.shard_chains(64, world, r) for r in range(world)]
+        assert sorted(sum(owned, [])) == list(range(64))
+        assert all(len(x) == 64 // world for x in owned)
+    assert parallel.shard_chains(5, 2, 0) == [0, 2, 4] and parallel.shard_chains(5, 2, 1) == [1, 3]
+    assert parallel.chain_seed(1, 3) == 4
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_chains = 5
+    ids = parallel.shard_chains(n_chains, world, rank)
+    local = torch.stack([torch.full((3, 4), complex(c, -c), dtype=torch.complex128) for c in ids])
+    full = parallel.gather_samples(local, n_chains, world)
+    ok = all(bool((full[c] == complex(c, -c)).all()) for c in range(n_chains))
+    acc = parallel.pooled_acceptance(accepted_local=rank + 1, steps_local=10)
+    q.put((rank, ok, acc))
+    dist.destroy_process_group()
+
+
+def test_gather_samples_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res)
+    assert all(abs(acc - 3 / 20) < 1e-12 for _, _, acc in res)
