@@ -84,7 +84,7 @@ typedef struct {
     double log_u;                   /* log of the accept uniform */
 } mspde_step_noise;
 
-enum { MSPDE_STEP_CACHE_PHI_CUR = 1, MSPDE_STEP_SKIP_GIBBS = 2 };
+enum { MSPDE_STEP_CACHE_PHI_CUR = 1, MSPDE_STEP_SKIP_GIBBS = 2, MSPDE_STEP_SERIAL = 4 /* one stream, no task overlap */ };
 
 /* out_dev (device, 4 doubles) <- {accepted (0/1), logRatio, Phi_cur, Phi_new}; record_dev (optional) <-
  * n_layers x n_ravel current half samples (Layer.record_sample, 792-795). */

@@ -64,16 +64,24 @@ int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n
     CTX_ALLOC(G, size_t(2) * m * n);
     CTX_ALLOC(tp, size_t(il) * il);
     CTX_ALLOC(tm, size_t(il) * il);
-    CTX_ALLOC(r, size_t(N) * c.ldN);
-    CTX_ALLOC(X, size_t(N) * c.ldM);
-    CTX_ALLOC(Q, size_t(M) * c.ldM);
-    CTX_ALLOC(winv, winv_elems(N > M ? N : M));
-    CTX_ALLOC(rowsq, M);
-    CTX_ALLOC(rowlog, M);
+    for (int s = 0; s < 2; ++s) {
+        CTX_ALLOC(pw[s].r, size_t(N) * c.ldN);
+        CTX_ALLOC(pw[s].X, size_t(N) * c.ldM);
+        CTX_ALLOC(pw[s].Q, size_t(M) * c.ldM);
+        CTX_ALLOC(pw[s].winv, winv_elems(N > M ? N : M));
+        CTX_ALLOC(pw[s].rowsq, M);
+        CTX_ALLOC(pw[s].rowlog, M);
+    }
+    MSPDE_CUDA(cudaStreamCreateWithFlags(&c.s1, cudaStreamNonBlocking));
+    MSPDE_CUDA(cudaStreamCreateWithFlags(&c.s2, cudaStreamNonBlocking));
+    MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_start, cudaEventDisableTiming));
+    MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_L, cudaEventDisableTiming));
+    MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_s1, cudaEventDisableTiming));
+    MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_s2, cudaEventDisableTiming));
     CTX_ALLOC(scal, 64);
     CTX_ALLOC(info, 4);
     CTX_ALLOC(vecN, size_t(4) * (N + M));
-    c.ldA = round_up(N + 1, 8);
+    c.ldA = round_up(N + 2, 8);
     CTX_ALLOC(QRaug, size_t(M + N) * c.ldA);
     {
         unsigned char* w = nullptr;
@@ -95,6 +103,10 @@ int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n
 
 int mspde_ctx_destroy(mspde_ctx* h) {
     if (!h) return 0;
+    if (h->c.s1) cudaStreamDestroy(h->c.s1);
+    if (h->c.s2) cudaStreamDestroy(h->c.s2);
+    for (cudaEvent_t e : {h->c.ev_start, h->c.ev_L, h->c.ev_s1, h->c.ev_s2})
+        if (e) cudaEventDestroy(e);
     for (void* p : h->owned) cudaFree(p);
     delete h;
     return 0;
@@ -183,7 +195,7 @@ int mspde_construct_L(mspde_ctx* h, const void* u_sym, double sqrt_beta, void* L
 }
 
 int mspde_phi(mspde_ctx* h, const void* L, int ldl, double* out3_dev) {
-    return phi_eval(&h->c, (const cplx*)L, ldl, out3_dev);
+    return phi_eval(&h->c, h->c.stream, h->c.pw[0], (const cplx*)L, ldl, out3_dev);
 }
 
 int mspde_solve(mspde_ctx* h, const void* L, int ldl, const void* rhs, void* x, double* logabsdet_dev) {

@@ -6,6 +6,15 @@
 
 namespace mspde {
 
+struct PhiWork {
+    cplx* r = nullptr;        // N x ldN
+    cplx* X = nullptr;        // N x ldM   Ht = c^-1 H^H
+    cplx* Q = nullptr;        // M x ldM
+    cplx* winv = nullptr;     // inverses of 64-blocks, sized for max(N, M)
+    double* rowsq = nullptr;  // M
+    double* rowlog = nullptr; // M
+};
+
 struct Ctx {
     int device = 0;
     int n = 0, n_ext = 0, il = 0, N = 0, n_ravel = 0, m = 0, M = 0, n_layers = 0;
@@ -30,13 +39,12 @@ struct Ctx {
     cplx* tp = nullptr;       // il x il  sym2D(rfft2(exp(+u)))
     cplx* tm = nullptr;       // il x il
 
-    // Phi workspace
-    cplx* r = nullptr;        // N x ldN
-    cplx* X = nullptr;        // N x ldM   Ht = c^-1 H^H
-    cplx* Q = nullptr;        // M x ldM
-    cplx* winv = nullptr;     // inverses of 64-blocks, sized for max(N, M)
-    double* rowsq = nullptr;  // M
-    double* rowlog = nullptr; // M
+    // Phi workspaces: two sets so that Phi(L_current) and Phi(L_latest) can run on concurrent streams
+    PhiWork pw[2];
+    cplx*& r = pw[0].r;       // aliases of set 0 (debug / parity access)
+    cplx*& X = pw[0].X;
+    cplx*& Q = pw[0].Q;
+    cplx*& winv = pw[0].winv;
     double* scal = nullptr;   // small device scalars (phi triples, logdet, flags)
     int* info = nullptr;      // device LAPACK-style info
 
@@ -44,7 +52,11 @@ struct Ctx {
     cplx* QRaug = nullptr;    // (M+N) x ldA,  ldA = round8(N+1)
     int ldA = 0;
     void* qr_work = nullptr;
-    cplx* vecN = nullptr;     // scratch vectors
+    cplx* vecN = nullptr;     // scratch vectors (4 x (N+M))
+
+    // side streams for the independent heavy tasks of one step (Phi(L_current), Gibbs QR) and their events
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_L = nullptr, ev_s1 = nullptr, ev_s2 = nullptr;
 };
 
 // pcn.cu
@@ -57,6 +69,6 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
 int field_coeffs(Ctx* c, const cplx* u_sym, cplx* tp_out, cplx* tm_out);
 int assemble_L(Ctx* c, const cplx* tp, const cplx* tm, double sqrt_beta, cplx* L, int ldl);
 // phi.cu
-int phi_eval(Ctx* c, const cplx* L, int ldl, double* out3);   // out3 (device): phi, quad, logdet
+int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3);   // out3 (device): phi, quad, logdet
 
 }  // namespace mspde

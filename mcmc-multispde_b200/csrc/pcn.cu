@@ -67,17 +67,6 @@ __global__ void set_col_kernel(cplx* __restrict__ A, int lda, int col, const cpl
     if (i < rows) A[size_t(i) * lda + col] = b[i];
 }
 
-// column `col` of the stacked Gibbs system <- [y - e ; -noise_new]   (image_cupy.py:449, 584-586, 597)
-__global__ void gibbs_rhs_kernel(cplx* __restrict__ A, int lda, int col, const double* __restrict__ y,
-                                 const double* __restrict__ e, const cplx* __restrict__ noise, int M, int N) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < M) A[size_t(i) * lda + col] = make_double2(y[i] - e[i], 0.0);
-    else if (i < M + N) {
-        const cplx w = noise[i - M];
-        A[size_t(i) * lda + col] = make_double2(0.0 - w.x, 0.0 - w.y);
-    }
-}
-
 __global__ void record_kernel(const cplx* __restrict__ u_sym, int nr, cplx* __restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < nr) out[j] = u_sym[nr - 1 + j];   // current_sample = sym[n_ravel-1:]  (image_cupy.py:564, 794)
@@ -125,13 +114,67 @@ int gibbs_lstsq(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* v) {
     return lstsq_qr_aug(c->stream, c->QRaug, c->ldA, M + N, N, c->qr_work, v, nullptr);
 }
 
+namespace {
+// noise_new candidates of the last layer for both outcomes of the accept test (A.5: line 583 uses noise_cur AFTER the
+// accept copy): accepted -> base = previous noise_new, rejected -> base = noise_cur.  Column N / N+1 of the stacked
+// system get the matching right-hand sides [y - e ; -candidate].
+__global__ void gibbs_candidates_kernel(const cplx* __restrict__ noise_cur, const cplx* __restrict__ noise_new_prev,
+                                        const cplx* __restrict__ w_half, double beta, double betaZ, int N, int nr, int M,
+                                        const double* __restrict__ y, const double* __restrict__ e,
+                                        cplx* __restrict__ cand_acc, cplx* __restrict__ cand_rej, cplx* __restrict__ A, int lda) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) {
+        const cplx v = make_double2(y[i] - e[i], 0.0);
+        A[size_t(i) * lda + N] = v;
+        A[size_t(i) * lda + N + 1] = v;
+    } else if (i < M + N) {
+        const int j = i - M;
+        const cplx w = sym_at(w_half, j, nr);
+        const cplx ca = noise_new_prev[j], cr = noise_cur[j];
+        const cplx va = make_double2(betaZ * ca.x + beta * w.x, betaZ * ca.y + beta * w.y);
+        const cplx vr = make_double2(betaZ * cr.x + beta * w.x, betaZ * cr.y + beta * w.y);
+        cand_acc[j] = va;
+        cand_rej[j] = vr;
+        A[size_t(i) * lda + N] = make_double2(0.0 - va.x, 0.0 - va.y);
+        A[size_t(i) * lda + N + 1] = make_double2(0.0 - vr.x, 0.0 - vr.y);
+    }
+}
+
+// dst <- (*flag != 0) ? a : b
+__global__ void select_kernel(const double* __restrict__ flag, const cplx* __restrict__ a, const cplx* __restrict__ b,
+                              cplx* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (*flag != 0.0) ? a[i] : b[i];
+}
+
+}  // namespace
+
 int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flags, double* out_dev, cplx* record_dev) {
     cudaStream_t st = c->stream;
+    const bool serial = (flags & MSPDE_STEP_SERIAL) != 0;
+    cudaStream_t s1 = serial ? st : c->s1, s2 = serial ? st : c->s2;
     const int K = ch->n_layers, N = c->N, M = c->M, nr = c->n_ravel;
     const int nb = (N + 255) / 256;
     double* phi_cur3 = c->scal + 8;
     double* phi_new3 = c->scal + 12;
+    cplx* cand_acc = c->vecN;
+    cplx* cand_rej = c->vecN + N;
+    cplx* v_acc = c->vecN + 2 * size_t(N);
+    cplx* v_rej = c->vecN + 3 * size_t(N);
+    const bool do_gibbs = !(flags & MSPDE_STEP_SKIP_GIBBS);
     int rc;
+    // ---- stream s1: Phi(L_current) only depends on the previous step (image_cupy.py:567-568)
+    const bool cached = (flags & MSPDE_STEP_CACHE_PHI_CUR) && ch->phi_cur_valid;
+    if (!cached) {
+        if (!serial) {
+            MSPDE_CUDA(cudaEventRecord(c->ev_start, st));
+            MSPDE_CUDA(cudaStreamWaitEvent(s1, c->ev_start, 0));
+        }
+        rc = phi_eval(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3);
+        if (rc) return rc;
+        if (!serial) MSPDE_CUDA(cudaEventRecord(c->ev_s1, s1));
+    }
+    // ---- main stream: layers 0..K-2 (557-564)
     for (int k = 0; k < K - 1; ++k) {
         propose_kernel<<<nb, 256, 0, st>>>((const cplx*)ch->noise_cur[k], (const cplx*)nz->w_half[k], ch->beta, ch->betaZ, N,
                                            nr, (cplx*)ch->noise_new[k], k == 0 ? c->stdev_sym : nullptr,
@@ -147,20 +190,49 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
             if (rc) return rc;
         }
     }
-    const bool cached = (flags & MSPDE_STEP_CACHE_PHI_CUR) && ch->phi_cur_valid;
-    if (!cached) {
-        rc = phi_eval(c, (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3);
-        if (rc) return rc;
-    }
-    rc = field_coeffs(c, (const cplx*)ch->u_new[K - 2], c->tp, c->tm);
+    rc = field_coeffs(c, (const cplx*)ch->u_new[K - 2], c->tp, c->tm);                                   // 570
     if (rc) return rc;
     rc = assemble_L(c, c->tp, c->tm, ch->sqrt_betas[K - 1], (cplx*)ch->L_latest[K - 1], ch->ldl);
     if (rc) return rc;
-    rc = phi_eval(c, (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3);
+    // ---- stream s2: Gibbs least squares on [H; L_latest] with both candidate right-hand sides (583-599)
+    if (do_gibbs) {
+        if (!serial) {
+            MSPDE_CUDA(cudaEventRecord(c->ev_L, st));
+            MSPDE_CUDA(cudaStreamWaitEvent(s2, c->ev_L, 0));
+        }
+        rc = copy2d(s2, c->QRaug, c->ldA, c->H, c->ldH, M, N);
+        if (rc) return rc;
+        rc = copy2d(s2, c->QRaug + size_t(M) * c->ldA, c->ldA, (const cplx*)ch->L_latest[K - 1], ch->ldl, N, N);
+        if (rc) return rc;
+        gibbs_candidates_kernel<<<(M + N + 255) / 256, 256, 0, s2>>>((const cplx*)ch->noise_cur[K - 1],
+                                                                    (const cplx*)ch->noise_new[K - 1], (const cplx*)nz->w_last,
+                                                                    ch->beta, ch->betaZ, N, nr, M, c->y, nz->e, cand_acc,
+                                                                    cand_rej, c->QRaug, c->ldA);
+        MSPDE_LAUNCH_CHECK();
+        rc = geqrf_aug(s2, c->QRaug, c->ldA, M + N, N, 2, c->qr_work, nullptr);
+        if (rc) return rc;
+        rc = trsv_upper_aug(s2, c->QRaug, c->ldA, N, N, v_acc);
+        if (rc) return rc;
+        rc = trsv_upper_aug(s2, c->QRaug, c->ldA, N, N + 1, v_rej);
+        if (rc) return rc;
+        if (!serial) MSPDE_CUDA(cudaEventRecord(c->ev_s2, s2));
+    } else {
+        gibbs_candidates_kernel<<<(M + N + 255) / 256, 256, 0, st>>>((const cplx*)ch->noise_cur[K - 1],
+                                                                    (const cplx*)ch->noise_new[K - 1], (const cplx*)nz->w_last,
+                                                                    ch->beta, ch->betaZ, N, nr, M, c->y, nz->e, cand_acc,
+                                                                    cand_rej, c->QRaug, c->ldA);
+        MSPDE_LAUNCH_CHECK();
+    }
+    // ---- main stream: Phi(L_latest) (571), then join
+    rc = phi_eval(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3);
     if (rc) return rc;
-    accept_kernel<<<1, 32, 0, st>>>(phi_cur3, phi_new3, nz->log_u, out_dev);
+    if (!serial) {
+        if (!cached) MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_s1, 0));
+        if (do_gibbs) MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_s2, 0));
+    }
+    accept_kernel<<<1, 32, 0, st>>>(phi_cur3, phi_new3, nz->log_u, out_dev);                              // 573
     MSPDE_LAUNCH_CHECK();
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K; ++k) {                                                                        // 575-579
         cond_copy_kernel<<<nb, 256, 0, st>>>(out_dev, (const double2*)ch->u_new[k], (double2*)ch->u_cur[k], N);
         cond_copy_kernel<<<nb, 256, 0, st>>>(out_dev, (const double2*)ch->noise_new[k], (double2*)ch->noise_cur[k], N);
         if (k >= 1)
@@ -169,20 +241,10 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
     }
     cond_copy_scalar_kernel<<<1, 32, 0, st>>>(out_dev, phi_new3, phi_cur3, 3);   // keeps a cached Phi(current) in step
     MSPDE_LAUNCH_CHECK();
-    // Gibbs part: uses noise_cur after the accept copy and L_latest even after a rejection (Appendix A.4-3)
-    propose_kernel<<<nb, 256, 0, st>>>((const cplx*)ch->noise_cur[K - 1], (const cplx*)nz->w_last, ch->beta, ch->betaZ, N,
-                                       nr, (cplx*)ch->noise_new[K - 1], nullptr, nullptr);
+    // last layer: noise_new and the Gibbs draw that match the accept outcome
+    select_kernel<<<nb, 256, 0, st>>>(out_dev, cand_acc, cand_rej, (cplx*)ch->noise_new[K - 1], N);
+    if (do_gibbs) select_kernel<<<nb, 256, 0, st>>>(out_dev, v_acc, v_rej, (cplx*)ch->u_new[K - 1], N);
     MSPDE_LAUNCH_CHECK();
-    if (!(flags & MSPDE_STEP_SKIP_GIBBS)) {
-        rc = copy2d(st, c->QRaug, c->ldA, c->H, c->ldH, M, N);
-        if (rc) return rc;
-        rc = copy2d(st, c->QRaug + size_t(M) * c->ldA, c->ldA, (const cplx*)ch->L_latest[K - 1], ch->ldl, N, N);
-        if (rc) return rc;
-        gibbs_rhs_kernel<<<(M + N + 255) / 256, 256, 0, st>>>(c->QRaug, c->ldA, N, c->y, nz->e, (const cplx*)ch->noise_new[K - 1], M, N);
-        MSPDE_LAUNCH_CHECK();
-        rc = lstsq_qr_aug(st, c->QRaug, c->ldA, M + N, N, c->qr_work, (cplx*)ch->u_new[K - 1], nullptr);
-        if (rc) return rc;
-    }
     if (record_dev) {
         for (int k = 0; k < K; ++k) {
             record_kernel<<<(nr + 255) / 256, 256, 0, st>>>((const cplx*)ch->u_cur[k], nr, record_dev + size_t(k) * nr);

@@ -79,31 +79,30 @@ __global__ void __launch_bounds__(1024) phi_reduce_kernel(const double* __restri
 
 }  // namespace
 
-int phi_eval(Ctx* c, const cplx* L, int ldl, double* out3) {
-    cudaStream_t st = c->stream;
+int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3) {
     const int N = c->N, M = c->M;
     // r = HtH + delta I + L^H L (upper triangle)
-    init_r_kernel<<<dim3((N + 255) / 256, N), 256, 0, st>>>(c->HtH, c->ldHtH, c->delta, c->r, c->ldN, N);
+    init_r_kernel<<<dim3((N + 255) / 256, N), 256, 0, st>>>(c->HtH, c->ldHtH, c->delta, w.r, c->ldN, N);
     MSPDE_LAUNCH_CHECK();
-    int rc = zgemm_tn(st, true, N, N, N, 1.0, L, ldl, L, ldl, 1.0, c->r, c->ldN, GEMM_UPPER);
+    int rc = zgemm_tn(st, true, N, N, N, 1.0, L, ldl, L, ldl, 1.0, w.r, c->ldN, GEMM_UPPER);
     if (rc) return rc;
-    rc = potrf_upper(st, c->r, c->ldN, N, c->winv, c->info);
+    rc = potrf_upper(st, w.r, c->ldN, N, w.winv, c->info);
     if (rc) return rc;
     // X = U^-H H^H  (= c^-1 H^H = Ht)
-    MSPDE_CUDA(cudaMemcpy2DAsync(c->X, size_t(c->ldM) * sizeof(cplx), c->Hct, size_t(c->ldHct) * sizeof(cplx),
+    MSPDE_CUDA(cudaMemcpy2DAsync(w.X, size_t(c->ldM) * sizeof(cplx), c->Hct, size_t(c->ldHct) * sizeof(cplx),
                                  size_t(M) * sizeof(cplx), N, cudaMemcpyDeviceToDevice, st));
-    rc = trsm_uh(st, c->r, c->ldN, c->winv, N, c->X, c->ldM, M);
+    rc = trsm_uh(st, w.r, c->ldN, w.winv, N, w.X, c->ldM, M);
     if (rc) return rc;
     // Q_inv = I - X^H X (upper triangle)
-    rc = zgemm_tn(st, true, M, M, N, -1.0, c->X, c->ldM, c->X, c->ldM, 0.0, c->Q, c->ldM, GEMM_UPPER);
+    rc = zgemm_tn(st, true, M, M, N, -1.0, w.X, c->ldM, w.X, c->ldM, 0.0, w.Q, c->ldM, GEMM_UPPER);
     if (rc) return rc;
-    add_diag_kernel<<<(M + 255) / 256, 256, 0, st>>>(c->Q, c->ldM, M, 1.0);
+    add_diag_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.Q, c->ldM, M, 1.0);
     MSPDE_LAUNCH_CHECK();
-    rc = potrf_upper(st, c->Q, c->ldM, M, c->winv, c->info);
+    rc = potrf_upper(st, w.Q, c->ldM, M, w.winv, c->info);
     if (rc) return rc;
-    vy_kernel<<<(M + 7) / 8, 256, 0, st>>>(c->Q, c->ldM, c->y, M, c->rowsq, c->rowlog);
+    vy_kernel<<<(M + 7) / 8, 256, 0, st>>>(w.Q, c->ldM, c->y, M, w.rowsq, w.rowlog);
     MSPDE_LAUNCH_CHECK();
-    phi_reduce_kernel<<<1, 1024, 0, st>>>(c->rowsq, c->rowlog, M, out3);
+    phi_reduce_kernel<<<1, 1024, 0, st>>>(w.rowsq, w.rowlog, M, out3);
     MSPDE_LAUNCH_CHECK();
     return 0;
 }

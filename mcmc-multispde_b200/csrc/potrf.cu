@@ -171,7 +171,25 @@ int potrf_upper(cudaStream_t st, cplx* A, int lda, int n, cplx* winv, int* info)
                                         (int)(2 * NB * SP * sizeof(cplx))));
         g_attr = true;
     }
-    return potrf_rec(st, A, lda, n, 0, winv, info);
+    // Right-looking over wide panels (well-filled K = 512 trailing updates); each panel's diagonal block and the
+    // panel solve are recursive so that their flops are large-K GEMMs as well.
+    constexpr int NBO = 512;
+    for (int j0 = 0; j0 < n; j0 += NBO) {
+        const int jb = n - j0 < NBO ? n - j0 : NBO;
+        cplx* A11 = A + size_t(j0) * lda + j0;
+        cplx* wv = winv + size_t(j0 / NB) * NB * NB;
+        int rc = potrf_rec(st, A11, lda, jb, j0, wv, info);
+        if (rc) return rc;
+        const int rest = n - j0 - jb;
+        if (rest > 0) {
+            cplx* A12 = A11 + jb;
+            rc = trsm_uh(st, A11, lda, wv, jb, A12, lda, rest);
+            if (rc) return rc;
+            rc = zgemm_tn(st, true, rest, rest, jb, -1.0, A12, lda, A12, lda, 1.0, A11 + size_t(jb) * lda + jb, lda, GEMM_UPPER);
+            if (rc) return rc;
+        }
+    }
+    return 0;
 }
 
 }  // namespace mspde

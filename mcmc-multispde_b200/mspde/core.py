@@ -15,6 +15,7 @@ CDTYPE = torch.complex128
 
 STEP_CACHE_PHI_CUR = 1
 STEP_SKIP_GIBBS = 2
+STEP_SERIAL = 4
 
 
 class _Chain(ctypes.Structure):
