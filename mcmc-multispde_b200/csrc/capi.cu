@@ -72,8 +72,15 @@ int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n
         CTX_ALLOC(pw[s].rowsq, M);
         CTX_ALLOC(pw[s].rowlog, M);
     }
-    MSPDE_CUDA(cudaStreamCreateWithFlags(&c.s1, cudaStreamNonBlocking));
-    MSPDE_CUDA(cudaStreamCreateWithFlags(&c.s2, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;   // numerically lower = higher priority
+        MSPDE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const int mid = (hi + 1 <= lo) ? hi + 1 : lo;
+        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s0, cudaStreamNonBlocking, hi));    // solve -> Phi(latest): critical path
+        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s2, cudaStreamNonBlocking, mid));   // Gibbs QR
+        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s1, cudaStreamNonBlocking, lo));    // Phi(current): filler
+    }
+    MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_out, cudaEventDisableTiming));
     MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_start, cudaEventDisableTiming));
     MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_L, cudaEventDisableTiming));
     MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_s1, cudaEventDisableTiming));
@@ -103,6 +110,8 @@ int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n
 
 int mspde_ctx_destroy(mspde_ctx* h) {
     if (!h) return 0;
+    if (h->c.s0) cudaStreamDestroy(h->c.s0);
+    if (h->c.ev_out) cudaEventDestroy(h->c.ev_out);
     if (h->c.s1) cudaStreamDestroy(h->c.s1);
     if (h->c.s2) cudaStreamDestroy(h->c.s2);
     for (cudaEvent_t e : {h->c.ev_start, h->c.ev_L, h->c.ev_s1, h->c.ev_s2})

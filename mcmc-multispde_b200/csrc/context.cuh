@@ -55,8 +55,8 @@ struct Ctx {
     cplx* vecN = nullptr;     // scratch vectors (4 x (N+M))
 
     // side streams for the independent heavy tasks of one step (Phi(L_current), Gibbs QR) and their events
-    cudaStream_t s1 = nullptr, s2 = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_L = nullptr, ev_s1 = nullptr, ev_s2 = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr;   // main chain (highest priority), Phi(current), Gibbs
+    cudaEvent_t ev_start = nullptr, ev_L = nullptr, ev_s1 = nullptr, ev_s2 = nullptr, ev_out = nullptr;
 };
 
 // pcn.cu

@@ -150,9 +150,20 @@ __global__ void select_kernel(const double* __restrict__ flag, const cplx* __res
 }  // namespace
 
 int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flags, double* out_dev, cplx* record_dev) {
-    cudaStream_t st = c->stream;
     const bool serial = (flags & MSPDE_STEP_SERIAL) != 0;
+    cudaStream_t caller = c->stream;
+    cudaStream_t st = serial ? caller : c->s0;
+    struct StreamGuard {   // helpers (field_coeffs, assemble_L, solve_L) launch on c->stream: point it at the main chain
+        Ctx* c; cudaStream_t saved;
+        ~StreamGuard() { c->stream = saved; }
+    } guard{c, caller};
     cudaStream_t s1 = serial ? st : c->s1, s2 = serial ? st : c->s2;
+    if (!serial) {   // internal streams start after everything already queued on the caller's stream
+        MSPDE_CUDA(cudaEventRecord(c->ev_start, caller));
+        MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_start, 0));
+        MSPDE_CUDA(cudaStreamWaitEvent(s1, c->ev_start, 0));
+    }
+    c->stream = st;
     const int K = ch->n_layers, N = c->N, M = c->M, nr = c->n_ravel;
     const int nb = (N + 255) / 256;
     double* phi_cur3 = c->scal + 8;
@@ -166,10 +177,6 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
     // ---- stream s1: Phi(L_current) only depends on the previous step (image_cupy.py:567-568)
     const bool cached = (flags & MSPDE_STEP_CACHE_PHI_CUR) && ch->phi_cur_valid;
     if (!cached) {
-        if (!serial) {
-            MSPDE_CUDA(cudaEventRecord(c->ev_start, st));
-            MSPDE_CUDA(cudaStreamWaitEvent(s1, c->ev_start, 0));
-        }
         rc = phi_eval(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3);
         if (rc) return rc;
         if (!serial) MSPDE_CUDA(cudaEventRecord(c->ev_s1, s1));
@@ -250,6 +257,10 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
             record_kernel<<<(nr + 255) / 256, 256, 0, st>>>((const cplx*)ch->u_cur[k], nr, record_dev + size_t(k) * nr);
         }
         MSPDE_LAUNCH_CHECK();
+    }
+    if (!serial) {   // the caller's stream continues after the step
+        MSPDE_CUDA(cudaEventRecord(c->ev_out, st));
+        MSPDE_CUDA(cudaStreamWaitEvent(caller, c->ev_out, 0));
     }
     return 0;
 }

@@ -22,7 +22,6 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(cplx* __restrict__ A, i
                                                          cplx* __restrict__ winv, int* __restrict__ info) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     cplx* S = reinterpret_cast<cplx*>(sm_raw);          // U (upper) after factorisation   [NB][SP]
-    cplx* X = S + NB * SP;                              // inverse                          [NB][SP]
     __shared__ cplx rowbuf[2][NB];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
 
@@ -54,8 +53,8 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(cplx* __restrict__ A, i
             bad = true;   // not positive definite (or NaN): LAPACK zpotrf info = k+1
             if (tid == 0) atomicCAS(info, 0, goff + k + 1);
         }
-        const double d = sqrt(akk);
-        const double inv = 1.0 / d;
+        const double inv = rsqrt(akk);
+        const double d = akk * inv;
         cplx vi[4], vj[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) vi[a] = cscale(rowbuf[k & 1][ty + 16 * a], inv);
@@ -87,33 +86,31 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(cplx* __restrict__ A, i
             if (i < nb && j < nb && j >= i) A[size_t(i) * lda + j] = r[a][b];
         }
     __syncthreads();
-    // X = U^-1 by back substitution; 4 threads per column split the dot products
+    // In-place triangular inverse (ztrti2, columnwise): X[0:j, j] = -X[j][j] * (X[0:j,0:j] * U[0:j, j]), X[j][j] = 1/U[j][j].
+    // Row i of column j is a dot product over k = i..j-1, split over 4 consecutive lanes.
     {
-        const int col = tid >> 2, part = tid & 3;
-        for (int i = NB - 1; i >= 0; --i) {
+        const int row = tid >> 2, part = tid & 3;
+        for (int j = 0; j < NB; ++j) {
             cplx s = make_double2(0.0, 0.0);
-            if (i < col) {
-                for (int k = i + 1 + part; k <= col; k += 4) s = cfma(S[i * SP + k], X[k * SP + col], s);
+            if (row < j) {
+                for (int k = row + part; k < j; k += 4) s = cfma(S[row * SP + k], S[k * SP + j], s);
             }
             s.x += __shfl_xor_sync(0xffffffffu, s.x, 1);
             s.y += __shfl_xor_sync(0xffffffffu, s.y, 1);
             s.x += __shfl_xor_sync(0xffffffffu, s.x, 2);
             s.y += __shfl_xor_sync(0xffffffffu, s.y, 2);
+            const double xjj = 1.0 / S[j * SP + j].x;     // diagonal of a Cholesky factor is real
+            __syncthreads();                              // every dot product has read column j before it is overwritten
             if (part == 0) {
-                const double uii = S[i * SP + i].x;   // diagonal of a Cholesky factor is real
-                cplx x;
-                if (i > col) x = make_double2(0.0, 0.0);
-                else if (i == col) x = make_double2(1.0 / uii, 0.0);
-                else x = make_double2(-s.x / uii, -s.y / uii);
-                X[i * SP + col] = x;
+                if (row < j) S[row * SP + j] = make_double2(-xjj * s.x, -xjj * s.y);
+                else if (row == j) S[row * SP + j] = make_double2(xjj, 0.0);
             }
-            __syncwarp();
+            __syncthreads();
         }
     }
-    __syncthreads();
     for (int idx = tid; idx < NB * NB; idx += 256) {
         int i = idx >> 6, j = idx & 63;
-        winv[idx] = X[i * SP + j];
+        winv[idx] = (j >= i) ? S[i * SP + j] : make_double2(0.0, 0.0);
     }
 }
 
@@ -147,7 +144,7 @@ int trsm_uh(cudaStream_t st, const cplx* U, int ldu, const cplx* winv, int n, cp
 
 static int potrf_rec(cudaStream_t st, cplx* A, int lda, int n, int goff, cplx* winv, int* info) {
     if (n <= NB) {
-        potrf_diag_kernel<<<1, 256, 2 * NB * SP * sizeof(cplx), st>>>(A, lda, n, goff, winv, info);
+        potrf_diag_kernel<<<1, 256, NB * SP * sizeof(cplx), st>>>(A, lda, n, goff, winv, info);
         MSPDE_LAUNCH_CHECK();
         return 0;
     }
@@ -168,7 +165,7 @@ static int potrf_rec(cudaStream_t st, cplx* A, int lda, int n, int goff, cplx* w
 int potrf_upper(cudaStream_t st, cplx* A, int lda, int n, cplx* winv, int* info) {
     if (!g_attr) {
         MSPDE_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(2 * NB * SP * sizeof(cplx))));
+                                        (int)(NB * SP * sizeof(cplx))));
         g_attr = true;
     }
     // Right-looking over wide panels (well-filled K = 512 trailing updates); each panel's diagonal block and the

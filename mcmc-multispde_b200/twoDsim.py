@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Driver with the flag surface of /root/reference/twoDsim.py (argparse block 68-97) on top of mspde.image.
+
+Not carried over (out of the hot-path scope): FBP initialisation through skimage.iradon, HDF5 chain
+continuation, Slurm self-resubmission and post_analysis plotting.  `--chains` / torchrun adds the chain-parallel mode."""
+import argparse
+import datetime
+import os
+import pathlib
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from mspde import image as im      # noqa: E402
+
+
+def _str_to_bool(s):
+    if s.lower() not in ['true', 'false']:
+        raise ValueError('Need bool; got %r' % s)
+    return {'true': True, 'false': False}[s.lower()]
+
+
+def add_boolean_argument(parser, name, default=False, messages=""):
+    """parser_help.add_boolean_argument (/root/reference/parser_help.py:7-11)."""
+    group = parser.add_mutually_exclusive_group()
+    group.add_argument('--' + name, nargs='?', default=default, const=True, type=_str_to_bool, help=messages)
+    group.add_argument('--no' + name, dest=name, action='store_false', help=messages)
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--iter', default=0, type=int)
+    parser.add_argument('--seq-no', default=0, type=int)
+    parser.add_argument('--n-layers', default=2, type=int)
+    parser.add_argument('--n-theta', default=45, type=int)
+    parser.add_argument('--n', default=32, type=int)
+    parser.add_argument('--seed', default=1, type=int)
+    parser.add_argument('--n-extended', default=64, type=int)
+    parser.add_argument('--n-samples', default=100, type=int)
+    parser.add_argument('--evaluation-interval', default=10, type=int)
+    parser.add_argument('--beta', default=1, type=float)
+    parser.add_argument('--kappa', default=5e9, type=float)
+    parser.add_argument('--chol-epsilon', default=1e-6, type=float)
+    parser.add_argument('--sigma-0', default=4e7, type=float)
+    parser.add_argument('--sigma-v', default=3.2e4, type=float)
+    parser.add_argument('--meas-std', default=0.2, type=float)
+    parser.add_argument('--sigma-scaling', default=4e-1, type=float)
+    parser.add_argument('--burn-percentage', default=25.0, type=float)
+    parser.add_argument('--variant', default="dunlop", type=str)
+    parser.add_argument('--phantom-name', default="shepp.png", type=str)
+    parser.add_argument('--meas-type', default="tomo", type=str)
+    parser.add_argument('--init-folder', default="", type=str)
+    parser.add_argument('--result-dir', default="", type=str, help='where result_<seq>.npz is written (default ./SimulationResult)')
+    add_boolean_argument(parser, 'naive', default=False)
+    add_boolean_argument(parser, 'enable-step-adaptation', default=True)
+    add_boolean_argument(parser, 'print-progress', default=True)
+    add_boolean_argument(parser, 'verbose', default=True)
+    add_boolean_argument(parser, 'hybrid', default=False)
+    add_boolean_argument(parser, 'adapt-sqrtbeta', default=False)
+    args = parser.parse_args(argv)
+    if args.n_theta == 18:                      # twoDsim.py:98-99
+        args.seed = 2
+    if args.adapt_sqrtbeta or args.naive:
+        raise NotImplementedError("--adapt-sqrtbeta / --naive are SURVEY 8(f2) items and are not built yet")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sim = im.Simulation(n_layers=args.n_layers, n_samples=args.n_samples, n=args.n, n_extended=args.n_extended, beta=args.beta,
+                        kappa=args.kappa, sigma_0=args.sigma_0, sigma_v=args.sigma_v, sigma_scaling=args.sigma_scaling,
+                        meas_std=args.meas_std, evaluation_interval=args.evaluation_interval, printProgress=args.print_progress,
+                        seed=args.seed + int(os.environ.get("RANK", "0")), burn_percentage=args.burn_percentage,
+                        enable_step_adaptation=args.enable_step_adaptation, pcn_variant=args.variant,
+                        phantom_name=args.phantom_name, meas_type=args.meas_type, n_theta=args.n_theta, verbose=args.verbose,
+                        hybrid_GPU_CPU=args.hybrid, device=local_rank)
+    sim.pcn.set_chol_epsilon(args.chol_epsilon)                 # twoDsim.py:106
+    sim.pcn.target_acceptance_rate = 0.234                      # twoDsim.py:107
+    parent = pathlib.Path(args.result_dir) if args.result_dir else pathlib.Path.cwd() / 'SimulationResult'
+    folder = parent / ('result-' + datetime.datetime.now().strftime('%d-%b-%Y_%H_%M_%S') if args.seq_no == 0 else args.init_folder)
+    folder.mkdir(parents=True, exist_ok=True)
+    sim.run()
+    out = folder / 'result_{}_rank{}.npz'.format(args.seq_no, os.environ.get("RANK", "0"))
+    sim.save(str(out))
+    print('simulation result stored in {} ({:.2f} it/s, acceptance {:.1%})'.format(
+        out, args.n_samples / max(sim.total_time, 1e-9), sim.acceptancePercentage))
+
+
+if __name__ == '__main__':
+    main()
