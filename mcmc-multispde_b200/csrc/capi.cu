@@ -76,9 +76,17 @@ int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n
         int lo = 0, hi = 0;   // numerically lower = higher priority
         MSPDE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         const int mid = (hi + 1 <= lo) ? hi + 1 : lo;
-        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s0, cudaStreamNonBlocking, hi));    // solve -> Phi(latest): critical path
-        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s2, cudaStreamNonBlocking, mid));   // Gibbs QR
-        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s1, cudaStreamNonBlocking, lo));    // Phi(current): filler
+        auto lvl = [&](int k) { int p = hi + k; return p > lo ? lo : p; };   // k = 0 highest
+        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s0, cudaStreamNonBlocking, lvl(0)));    // solve -> Phi(latest): critical path
+        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s2, cudaStreamNonBlocking, lvl(1)));    // Gibbs QR
+        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.pw[0].la.aux, cudaStreamNonBlocking, lvl(2)));   // trailing HERKs of Phi(latest)
+        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s1, cudaStreamNonBlocking, lvl(3)));    // Phi(current): filler
+        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.pw[1].la.aux, cudaStreamNonBlocking, lvl(4)));
+        for (int s = 0; s < 2; ++s) {
+            MSPDE_CUDA(cudaEventCreateWithFlags(&c.pw[s].la.ev_a, cudaEventDisableTiming));
+            MSPDE_CUDA(cudaEventCreateWithFlags(&c.pw[s].la.ev_b, cudaEventDisableTiming));
+        }
+        (void)mid;
     }
     MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_out, cudaEventDisableTiming));
     MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_start, cudaEventDisableTiming));
@@ -204,7 +212,7 @@ int mspde_construct_L(mspde_ctx* h, const void* u_sym, double sqrt_beta, void* L
 }
 
 int mspde_phi(mspde_ctx* h, const void* L, int ldl, double* out3_dev) {
-    return phi_eval(&h->c, h->c.stream, h->c.pw[0], (const cplx*)L, ldl, out3_dev);
+    return phi_eval(&h->c, h->c.stream, h->c.pw[0], (const cplx*)L, ldl, out3_dev, false);
 }
 
 int mspde_solve(mspde_ctx* h, const void* L, int ldl, const void* rhs, void* x, double* logabsdet_dev) {

@@ -13,6 +13,7 @@ struct PhiWork {
     cplx* winv = nullptr;     // inverses of 64-blocks, sized for max(N, M)
     double* rowsq = nullptr;  // M
     double* rowlog = nullptr; // M
+    LookAhead la;             // look-ahead stream/events of this workspace's Cholesky factorizations
 };
 
 struct Ctx {
@@ -69,6 +70,6 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
 int field_coeffs(Ctx* c, const cplx* u_sym, cplx* tp_out, cplx* tm_out);
 int assemble_L(Ctx* c, const cplx* tp, const cplx* tm, double sqrt_beta, cplx* L, int ldl);
 // phi.cu
-int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3);   // out3 (device): phi, quad, logdet
+int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3, bool serial = false);   // out3 (device): phi, quad, logdet
 
 }  // namespace mspde

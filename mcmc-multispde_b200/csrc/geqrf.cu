@@ -35,17 +35,41 @@ struct QrWork {
     cplx* tau;    // PW
     cplx* dots;   // 2 x MAXG x PW   per-CTA partial dot products (double buffered)
     cplx* currow; // 2 x PW          current diagonal row (double buffered)
+    unsigned* bar; // grid barrier counter
     int ldvt, ldw, nsplit;
 };
 
 size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
+// split-K partial products: up to 148 slices of the 64 x 64 Gram matrix, or ~10 slices of the 64 x (cols+1) W panel
+size_t part_elems(int cols) {
+    const size_t ldw = (cols + 1 + 7) / 8 * 8;
+    const size_t a = size_t(149) * PW * PW, b = size_t(12) * PW * ldw;
+    return a > b ? a : b;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Grid-wide barrier on a monotonically increasing counter (zeroed before the launch).  Data exchanged across it is
+// written with plain stores before the barrier and read with ld.global.cg (L1 bypass) after it.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (ld_acquire_u32(counter) < target) {}
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ cplx ldcg(const cplx* p) { return __ldcg(p); }
 
 // Panel: A[c0 + (0..mp-1)][c0 + (0..pw-1)], pw <= PW pivot columns.
 __global__ void __launch_bounds__(256) qr_panel_kernel(cplx* __restrict__ A, int lda, int mp, int pw, int slab,
                                                        cplx* __restrict__ V, cplx* __restrict__ Vt, int ldvt,
-                                                       cplx* __restrict__ tau_out, cplx* __restrict__ dots,
-                                                       cplx* __restrict__ currow, double* __restrict__ logabs) {
-    cg::grid_group grid = cg::this_grid();
+                                                       cplx* __restrict__ tau_out, cplx* dots, cplx* currow,
+                                                       double* __restrict__ logabs, unsigned* barrier_counter) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     cplx* S = reinterpret_cast<cplx*>(sm_raw);   // [slab][SPITCH]
     __shared__ cplx red[4][PW];
@@ -62,34 +86,70 @@ __global__ void __launch_bounds__(256) qr_panel_kernel(cplx* __restrict__ A, int
     }
     __syncthreads();
 
+#ifdef MSPDE_QR_PROFILE
+    long long tA = 0, tB = 0, tC = 0, tD = 0, t0, t1;
+#define TICK(acc) t1 = clock64(); acc += t1 - t0; t0 = t1;
+    t0 = clock64();
+#else
+#define TICK(acc)
+#endif
     for (int j = 0; j < pw; ++j) {
         const int buf = j & 1;
         // ---- partial dots over rows strictly below the diagonal row j:  sum_i conj(a[i][j]) a[i][j'] , j' >= j
         cplx acc = make_double2(0.0, 0.0);
         if (tx >= j && tx < pw) {
             const int lo = max(0, j + 1 - row0);
-            for (int i = lo + ty; i < nrow; i += 4) acc = cfmac(S[i * SPITCH + j], S[i * SPITCH + tx], acc);
+            cplx acc2 = make_double2(0.0, 0.0);
+            int i = lo + ty;
+            for (; i + 4 < nrow; i += 8) {
+                acc = cfmac(S[i * SPITCH + j], S[i * SPITCH + tx], acc);
+                acc2 = cfmac(S[(i + 4) * SPITCH + j], S[(i + 4) * SPITCH + tx], acc2);
+            }
+            if (i < nrow) acc = cfmac(S[i * SPITCH + j], S[i * SPITCH + tx], acc);
+            acc = cadd(acc, acc2);
         }
         red[ty][tx] = acc;
         __syncthreads();
         if (ty == 0) {
             cplx s = cadd(cadd(red[0][tx], red[1][tx]), cadd(red[2][tx], red[3][tx]));
-            dots[(size_t(buf) * MAXG + blockIdx.x) * PW + tx] = s;
+            dots[(size_t(buf) * PW + tx) * MAXG + blockIdx.x] = s;          // [column][cta]: coalesced for the readers
             if (j >= row0 && j < row0 + nrow) currow[buf * PW + tx] = S[(j - row0) * SPITCH + tx];
         }
-        grid.sync();
-        // ---- every CTA reduces the G partials in the same fixed order
+        TICK(tA)
+        grid_barrier(barrier_counter, unsigned(G) * unsigned(j + 1));
+        TICK(tB)
+        // ---- every CTA reduces the G partials of the live columns in the same fixed order: warp w takes columns
+        //      w, w+8, ...; lane l sums partials l, l+32, ... and a butterfly finishes.  All loads are issued first.
         {
-            cplx s = make_double2(0.0, 0.0);
-            for (int c = ty; c < G; c += 4) s = cadd(s, dots[(size_t(buf) * MAXG + c) * PW + tx]);
-            red[ty][tx] = s;
+            const int wrp = tid >> 5, ln = tid & 31;
+            cplx part[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const cplx* src = dots + (size_t(buf) * PW + (wrp + 8 * q)) * MAXG;     // columns < j hold stale, unused data
+                cplx v[5];
+#pragma unroll
+                for (int h = 0; h < 5; ++h) {
+                    const int cidx = ln + 32 * h;
+                    const bool live = (cidx < G) && (wrp + 8 * q >= j);
+                    v[h] = live ? ldcg(src + cidx) : make_double2(0.0, 0.0);
+                }
+                part[q] = cadd(cadd(cadd(v[0], v[1]), cadd(v[2], v[3])), v[4]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (wrp + 8 * q < j) continue;     // warp-uniform
+                cplx a = part[q];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+                    a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+                }
+                if (ln == 0) sdot[wrp + 8 * q] = a;
+            }
+            if (tid < PW) srow[tid] = ldcg(currow + buf * PW + tid);
         }
         __syncthreads();
-        if (ty == 0) {
-            sdot[tx] = cadd(cadd(red[0][tx], red[1][tx]), cadd(red[2][tx], red[3][tx]));
-            srow[tx] = currow[buf * PW + tx];
-        }
-        __syncthreads();
+        TICK(tC)
         // ---- zlarfg: alpha = a_jj, beta = -sign(Re alpha) * sqrt(|alpha|^2 + xnorm^2), tau = (beta - alpha)/beta
         const cplx alpha = srow[j];
         const double xn2 = sdot[j].x;
@@ -134,7 +194,11 @@ __global__ void __launch_bounds__(256) qr_panel_kernel(cplx* __restrict__ A, int
             }
         }
         __syncthreads();
+        TICK(tD)
     }
+#ifdef MSPDE_QR_PROFILE
+    if (tid == 0 && blockIdx.x == 0) printf("panel mp=%d G=%d pw=%d cycles/col: dots %lld sync %lld reduce %lld update %lld\n", mp, G, pw, tA / pw, tB / pw, tC / pw, tD / pw);
+#endif
     // ---- write back: R on/above the diagonal into A (reflector storage below it), explicit V and V^T to workspace
     for (int idx = tid; idx < nrow * PW; idx += 256) {
         const int i = idx >> 6, j = idx & 63;
@@ -161,28 +225,34 @@ __global__ void __launch_bounds__(256) qr_panel_kernel(cplx* __restrict__ A, int
 }
 
 // T[j][j] = tau_j ; T[0:j, j] = -tau_j * T[0:j,0:j] * (V^H V)[0:j, j]      (zlarft, forward, columnwise)
-__global__ void __launch_bounds__(PW) larft_kernel(const cplx* __restrict__ Gm, const cplx* __restrict__ tau, int pw,
-                                                   cplx* __restrict__ T) {
+// 256 threads: row a = tid/4, the dot product over b = a..j-1 is split over 4 consecutive lanes.
+__global__ void __launch_bounds__(256) larft_kernel(const cplx* __restrict__ Gm, const cplx* __restrict__ tau, int pw,
+                                                    cplx* __restrict__ T) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     cplx (*sT)[PW + 1] = reinterpret_cast<cplx (*)[PW + 1]>(sm_raw);
-    cplx* col = reinterpret_cast<cplx*>(sm_raw) + PW * (PW + 1);
-    const int a = threadIdx.x;
-    for (int b = 0; b < PW; ++b) sT[a][b] = make_double2(0.0, 0.0);
+    cplx (*sG)[PW + 1] = reinterpret_cast<cplx (*)[PW + 1]>(sm_raw + sizeof(cplx) * PW * (PW + 1));
+    const int tid = threadIdx.x, a = tid >> 2, part = tid & 3;
+    for (int idx = tid; idx < PW * PW; idx += 256) {
+        sT[idx >> 6][idx & 63] = make_double2(0.0, 0.0);
+        sG[idx >> 6][idx & 63] = Gm[idx];
+    }
     __syncthreads();
     for (int j = 0; j < pw; ++j) {
         const cplx tj = tau[j];
-        col[a] = (a < j) ? Gm[a * PW + j] : make_double2(0.0, 0.0);
-        __syncthreads();
-        if (a < j) {
-            cplx s = make_double2(0.0, 0.0);
-            for (int b = a; b < j; ++b) s = cfma(sT[a][b], col[b], s);
-            sT[a][j] = cmul(make_double2(-tj.x, -tj.y), s);
-        } else if (a == j) {
-            sT[a][j] = tj;
+        cplx s = make_double2(0.0, 0.0);
+        if (a < j)
+            for (int b = a + part; b < j; b += 4) s = cfma(sT[a][b], sG[b][j], s);
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, 1);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, 1);
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, 2);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, 2);
+        if (part == 0) {
+            if (a < j) sT[a][j] = cmul(make_double2(-tj.x, -tj.y), s);
+            else if (a == j) sT[a][j] = tj;
         }
         __syncthreads();
     }
-    for (int b = 0; b < PW; ++b) T[a * PW + b] = sT[a][b];
+    for (int idx = tid; idx < PW * PW; idx += 256) T[idx] = sT[idx >> 6][idx & 63];
 }
 
 // x_blk = R_bb^-1 d_blk for one 64-block (single CTA), R upper; d lives in column `dcol` of the same matrix
@@ -230,16 +300,17 @@ QrWork carve(void* work, int rows, int cols) {
     auto take = [&](size_t bytes) { void* q = p; p += align_up(bytes); return q; };
     w.ldvt = (rows + 7) / 8 * 8;
     w.ldw = (cols + 1 + 7) / 8 * 8;
-    w.nsplit = 6;
+    w.nsplit = 148;
     w.V = (cplx*)take(size_t(rows) * PW * sizeof(cplx));
     w.Vt = (cplx*)take(size_t(PW) * w.ldvt * sizeof(cplx));
     w.W = (cplx*)take(size_t(PW) * w.ldw * sizeof(cplx));
-    w.part = (cplx*)take(size_t(w.nsplit + 1) * PW * size_t(w.ldw > PW ? w.ldw : PW) * sizeof(cplx));
+    w.part = (cplx*)take(part_elems(cols) * sizeof(cplx));
     w.Gm = (cplx*)take(size_t(PW) * PW * sizeof(cplx));
     w.T = (cplx*)take(size_t(PW) * PW * sizeof(cplx));
     w.tau = (cplx*)take(size_t(PW) * sizeof(cplx));
     w.dots = (cplx*)take(size_t(2) * MAXG * PW * sizeof(cplx));
     w.currow = (cplx*)take(size_t(2) * PW * sizeof(cplx));
+    w.bar = (unsigned*)take(256);
     return w;
 }
 
@@ -253,7 +324,7 @@ size_t qr_work_bytes(int rows, int cols) {
     b += align_up(size_t(rows) * PW * sizeof(cplx));
     b += align_up(size_t(PW) * ldvt * sizeof(cplx));
     b += align_up(size_t(PW) * ldw * sizeof(cplx));
-    b += align_up(size_t(7) * PW * (ldw > PW ? ldw : PW) * sizeof(cplx));
+    b += align_up(part_elems(cols) * sizeof(cplx));
     b += 3 * align_up(size_t(PW) * PW * sizeof(cplx));
     b += align_up(size_t(2) * MAXG * PW * sizeof(cplx));
     b += align_up(size_t(2) * PW * sizeof(cplx));
@@ -265,7 +336,7 @@ size_t qr_work_bytes(int rows, int cols) {
 static int init_attrs() {
     if (!g_attr) {
         MSPDE_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MSPDE_CUDA(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
+        MSPDE_CUDA(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(cplx) * PW * (PW + 1))));
         MSPDE_CUDA(cudaFuncSetAttribute(trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
         g_attr = true;
     }
@@ -292,19 +363,30 @@ int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, v
         cplx* V = w.V; cplx* Vt = w.Vt; int ldvt = w.ldvt; cplx* tau = w.tau; cplx* dots = w.dots; cplx* currow = w.currow;
         int mp_ = mp, pw_ = pw, slab_ = slab, lda_ = lda;
         double* la = logabs;
-        void* args[] = {&Ap, &lda_, &mp_, &pw_, &slab_, &V, &Vt, &ldvt, &tau, &dots, &currow, &la};
+        unsigned* bar = w.bar;
+        MSPDE_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+        void* args[] = {&Ap, &lda_, &mp_, &pw_, &slab_, &V, &Vt, &ldvt, &tau, &dots, &currow, &la, &bar};
         MSPDE_CUDA(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(G), dim3(256), args, smem, st));
         ++g_launches;
         const int n2 = ntot - (c0 + pw);
         if (n2 <= 0) continue;
         // T from V^H V
-        int rc = zgemm_tn_splitk(st, true, PW, PW, mp, 1.0, w.V, PW, w.V, PW, 0.0, w.Gm, PW, w.part, w.nsplit);
+        int ns_g = (mp + 127) / 128;
+        if (ns_g > w.nsplit) ns_g = w.nsplit;
+        int rc = zgemm_tn_splitk(st, true, PW, PW, mp, 1.0, w.V, PW, w.V, PW, 0.0, w.Gm, PW, w.part, ns_g);
         if (rc) return rc;
-        larft_kernel<<<1, PW, SMALL_SMEM, st>>>(w.Gm, w.tau, pw, w.T);
+        larft_kernel<<<1, 256, 2 * sizeof(cplx) * PW * (PW + 1), st>>>(w.Gm, w.tau, pw, w.T);
         MSPDE_LAUNCH_CHECK();
         cplx* A2 = Ap + pw;
         // W = V^H A2
-        rc = zgemm_tn_splitk(st, true, PW, n2, mp, 1.0, w.V, PW, A2, lda, 0.0, w.W, w.ldw, w.part, w.nsplit);
+        const int tiles = (n2 + 63) / 64;
+        int ns_w = (592 + tiles - 1) / tiles;                 // ~2 waves of 296 resident CTAs
+        const int ns_cap = (mp + 255) / 256;                  // keep >= 256 k per slice
+        if (ns_w > ns_cap) ns_w = ns_cap;
+        const int ns_fit = int(part_elems(cols) / (size_t(PW) * size_t(n2)));
+        if (ns_w > ns_fit) ns_w = ns_fit;                     // partial-product workspace
+        if (ns_w < 1) ns_w = 1;
+        rc = zgemm_tn_splitk(st, true, PW, n2, mp, 1.0, w.V, PW, A2, lda, 0.0, w.W, w.ldw, w.part, ns_w);
         if (rc) return rc;
         // W <- T^H W (in place: single row tile)
         rc = zgemm_tn(st, true, PW, n2, PW, 1.0, w.T, PW, w.W, w.ldw, 0.0, w.W, w.ldw, GEMM_FULL);

@@ -10,7 +10,11 @@ inline int winv_blocks(int n) { return (n + LEAF - 1) / LEAF; }
 inline size_t winv_elems(int n) { return size_t(winv_blocks(n)) * LEAF * LEAF; }
 
 // potrf.cu
-int potrf_upper(cudaStream_t st, cplx* A, int lda, int n, cplx* winv, int* info);
+struct LookAhead {          // auxiliary stream + events for the panel look-ahead of potrf_upper
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+};
+int potrf_upper(cudaStream_t st, cplx* A, int lda, int n, cplx* winv, int* info, const LookAhead* la = nullptr);
 int trsm_uh(cudaStream_t st, const cplx* U, int ldu, const cplx* winv, int n, cplx* B, int ldb, int ncols);
 
 // geqrf.cu

@@ -177,7 +177,7 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
     // ---- stream s1: Phi(L_current) only depends on the previous step (image_cupy.py:567-568)
     const bool cached = (flags & MSPDE_STEP_CACHE_PHI_CUR) && ch->phi_cur_valid;
     if (!cached) {
-        rc = phi_eval(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3);
+        rc = phi_eval(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3, serial);
         if (rc) return rc;
         if (!serial) MSPDE_CUDA(cudaEventRecord(c->ev_s1, s1));
     }
@@ -231,7 +231,7 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
         MSPDE_LAUNCH_CHECK();
     }
     // ---- main stream: Phi(L_latest) (571), then join
-    rc = phi_eval(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3);
+    rc = phi_eval(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3, serial);
     if (rc) return rc;
     if (!serial) {
         if (!cached) MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_s1, 0));

@@ -79,14 +79,14 @@ __global__ void __launch_bounds__(1024) phi_reduce_kernel(const double* __restri
 
 }  // namespace
 
-int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3) {
+int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3, bool serial) {
     const int N = c->N, M = c->M;
     // r = HtH + delta I + L^H L (upper triangle)
     init_r_kernel<<<dim3((N + 255) / 256, N), 256, 0, st>>>(c->HtH, c->ldHtH, c->delta, w.r, c->ldN, N);
     MSPDE_LAUNCH_CHECK();
     int rc = zgemm_tn(st, true, N, N, N, 1.0, L, ldl, L, ldl, 1.0, w.r, c->ldN, GEMM_UPPER);
     if (rc) return rc;
-    rc = potrf_upper(st, w.r, c->ldN, N, w.winv, c->info);
+    rc = potrf_upper(st, w.r, c->ldN, N, w.winv, c->info, serial ? nullptr : &w.la);
     if (rc) return rc;
     // X = U^-H H^H  (= c^-1 H^H = Ht)
     MSPDE_CUDA(cudaMemcpy2DAsync(w.X, size_t(c->ldM) * sizeof(cplx), c->Hct, size_t(c->ldHct) * sizeof(cplx),
@@ -98,7 +98,7 @@ int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double
     if (rc) return rc;
     add_diag_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.Q, c->ldM, M, 1.0);
     MSPDE_LAUNCH_CHECK();
-    rc = potrf_upper(st, w.Q, c->ldM, M, w.winv, c->info);
+    rc = potrf_upper(st, w.Q, c->ldM, M, w.winv, c->info, serial ? nullptr : &w.la);
     if (rc) return rc;
     vy_kernel<<<(M + 7) / 8, 256, 0, st>>>(w.Q, c->ldM, c->y, M, w.rowsq, w.rowlog);
     MSPDE_LAUNCH_CHECK();

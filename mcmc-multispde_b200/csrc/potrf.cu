@@ -162,30 +162,71 @@ static int potrf_rec(cudaStream_t st, cplx* A, int lda, int n, int goff, cplx* w
 
 // In-place upper Cholesky of the Hermitian matrix whose upper triangle is stored in A (row-major).
 // winv must hold ceil(n/64) * 64*64 complex.  *info (device) receives the first failing column (1-based), 0 if ok.
-int potrf_upper(cudaStream_t st, cplx* A, int lda, int n, cplx* winv, int* info) {
+//
+// Right-looking over 512-wide panels (well-filled K = 512 trailing updates); each panel's diagonal block and panel
+// solve are recursive so that their flops are large-K GEMMs as well.  With a look-ahead context the trailing update
+// of panel p is split: the block row of panel p+1 is updated on the main stream, the rest on an auxiliary
+// (lower-priority) stream, so that the latency-bound factorisation of panel p+1 runs underneath the big HERK.
+int potrf_upper(cudaStream_t st, cplx* A, int lda, int n, cplx* winv, int* info, const LookAhead* la) {
     if (!g_attr) {
         MSPDE_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(NB * SP * sizeof(cplx))));
         g_attr = true;
     }
-    // Right-looking over wide panels (well-filled K = 512 trailing updates); each panel's diagonal block and the
-    // panel solve are recursive so that their flops are large-K GEMMs as well.
     constexpr int NBO = 512;
+    const bool ahead = la && la->aux && n > 2 * NBO;
+    bool aux_pending = false;
     for (int j0 = 0; j0 < n; j0 += NBO) {
         const int jb = n - j0 < NBO ? n - j0 : NBO;
         cplx* A11 = A + size_t(j0) * lda + j0;
         cplx* wv = winv + size_t(j0 / NB) * NB * NB;
-        int rc = potrf_rec(st, A11, lda, jb, j0, wv, info);
-        if (rc) return rc;
         const int rest = n - j0 - jb;
-        if (rest > 0) {
-            cplx* A12 = A11 + jb;
-            rc = trsm_uh(st, A11, lda, wv, jb, A12, lda, rest);
+        // Panel phase, left-looking over the 64-row leaves of the panel: per leaf one wide update of its block row
+        // (all columns to the right, panel and trailing part alike), the diagonal-block kernel, and one wide row solve.
+        // 3 launches per leaf, every GEMM spans >= rest columns -- this replaces potrf_rec + trsm_uh on the panel.
+        int rc = 0;
+        for (int i0 = 0; i0 < jb; i0 += NB) {
+            const int ib = jb - i0 < NB ? jb - i0 : NB;
+            cplx* Aii = A11 + size_t(i0) * lda + i0;
+            const int right = (jb - i0) + rest;           // columns from the leaf's diagonal to the end of the matrix
+            if (i0 > 0) {
+                // A[i, i:] -= U[0:i0, i]^H U[0:i0, i:]   (upper part of the diagonal block only matters; full rows are fine)
+                rc = zgemm_tn(st, true, ib, right, i0, -1.0, A11 + i0, lda, A11 + i0, lda, 1.0, Aii, lda, GEMM_UPPER);
+                if (rc) return rc;
+            }
+            potrf_diag_kernel<<<1, 256, NB * SP * sizeof(cplx), st>>>(Aii, lda, ib, j0 + i0, wv + size_t(i0 / NB) * NB * NB, info);
+            MSPDE_LAUNCH_CHECK();
+            if (right > ib) {
+                rc = zgemm_tn(st, true, ib, right - ib, ib, 1.0, wv + size_t(i0 / NB) * NB * NB, NB, Aii + ib, lda, 0.0,
+                              Aii + ib, lda, GEMM_FULL);   // row solve, in place (single row tile)
+                if (rc) return rc;
+            }
+        }
+        if (rest <= 0) break;
+        cplx* A12 = A11 + jb;
+        cplx* A22 = A11 + size_t(jb) * lda + jb;
+        if (!ahead) {
+            rc = zgemm_tn(st, true, rest, rest, jb, -1.0, A12, lda, A12, lda, 1.0, A22, lda, GEMM_UPPER);
             if (rc) return rc;
-            rc = zgemm_tn(st, true, rest, rest, jb, -1.0, A12, lda, A12, lda, 1.0, A11 + size_t(jb) * lda + jb, lda, GEMM_UPPER);
+            continue;
+        }
+        const int nxt = rest < NBO ? rest : NBO;          // rows of the next panel
+        if (aux_pending) MSPDE_CUDA(cudaStreamWaitEvent(st, la->ev_b, 0));   // its block row got the previous (b) update
+        rc = zgemm_tn(st, true, nxt, rest, jb, -1.0, A12, lda, A12, lda, 1.0, A22, lda, GEMM_UPPER);          // (a)
+        if (rc) return rc;
+        if (rest > nxt) {
+            MSPDE_CUDA(cudaEventRecord(la->ev_a, st));
+            MSPDE_CUDA(cudaStreamWaitEvent(la->aux, la->ev_a, 0));
+            rc = zgemm_tn(la->aux, true, rest - nxt, rest - nxt, jb, -1.0, A12 + nxt, lda, A12 + nxt, lda, 1.0,
+                          A22 + size_t(nxt) * lda + nxt, lda, GEMM_UPPER);                                    // (b)
             if (rc) return rc;
+            MSPDE_CUDA(cudaEventRecord(la->ev_b, la->aux));
+            aux_pending = true;
+        } else {
+            aux_pending = false;
         }
     }
+    if (aux_pending) MSPDE_CUDA(cudaStreamWaitEvent(st, la->ev_b, 0));
     return 0;
 }
 

@@ -223,12 +223,25 @@ __global__ void splitk_reduce_kernel(const cplx* __restrict__ part, int nsplit, 
     long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= (long long)m * n) return;
     int i = int(idx / n), j = int(idx % n);
-    double sx = 0.0, sy = 0.0;
-    for (int s = 0; s < nsplit; ++s) {
-        cplx v = part[s * slice + idx];
-        sx += v.x;
-        sy += v.y;
+    // fixed summation order (deterministic); 8 independent accumulators keep 8 loads in flight
+    double ax[8], ay[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) ax[u] = ay[u] = 0.0;
+    int s = 0;
+    for (; s + 8 <= nsplit; s += 8) {
+        cplx v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = part[(s + u) * slice + idx];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { ax[u] += v[u].x; ay[u] += v[u].y; }
     }
+    for (; s < nsplit; ++s) {
+        cplx v = part[s * slice + idx];
+        ax[s & 7] += v.x;
+        ay[s & 7] += v.y;
+    }
+    const double sx = ((ax[0] + ax[1]) + (ax[2] + ax[3])) + ((ax[4] + ax[5]) + (ax[6] + ax[7]));
+    const double sy = ((ay[0] + ay[1]) + (ay[2] + ay[3])) + ((ay[4] + ay[5]) + (ay[6] + ay[7]));
     cplx* c = C + size_t(i) * ldc + j;
     cplx out = make_double2(alpha * sx, alpha * sy);
     if (beta != 0.0) {
