@@ -91,6 +91,13 @@ enum { MSPDE_STEP_CACHE_PHI_CUR = 1, MSPDE_STEP_SKIP_GIBBS = 2, MSPDE_STEP_SERIA
 int mspde_pcn_step(mspde_ctx* ctx, const mspde_chain* chain, const mspde_step_noise* noise, int flags, double* out_dev,
                    void* record_dev);
 
+/* f1 (setup): Sinogram.get_measurement_matrix (image_cupy.py:364-396) = the _calculate_H_Tomography kernel
+ * (mcmc/util_cupy.py:445-470) + ratio scaling (377-378) + roll fix (381-385) when apply_fixes != 0.
+ * r_flat / theta_flat are r_grid.ravel('F') / theta_grid.ravel('F') (length M, radians), ix / iy the 'F'-ravelled
+ * int32 index vectors (length N); H is M x N un-normalised. */
+int mspde_tomography_H(void* stream, int M, int N, const double* r_flat, const double* theta_flat, const int32_t* ix,
+                       const int32_t* iy, int n_r, int n_theta, int apply_fixes, void* H, int ldh);
+
 /* Building blocks (exported for the parity tests):
  * zgemm_tn  : C = alpha*opA(A)^T*B + beta*C, A k x m, B k x n  (cuBLAS ZGEMM call sites 634, 639)
  * zpotrf    : upper Cholesky A = U^H U                         (cuSOLVER ZPOTRF call sites 637, 642)

@@ -256,6 +256,11 @@ int mspde_zgemm_tn(void* stream, int conjA, int m, int n, int k, double alpha, c
     return zgemm_tn(st, conjA != 0, m, n, k, alpha, (const cplx*)A, lda, (const cplx*)B, ldb, beta, (cplx*)C, ldc, uplo);
 }
 
+int mspde_tomography_H(void* stream, int M, int N, const double* r_flat, const double* theta_flat, const int32_t* ix,
+                       const int32_t* iy, int n_r, int n_theta, int apply_fixes, void* H, int ldh) {
+    return tomography_H((cudaStream_t)stream, M, N, r_flat, theta_flat, ix, iy, n_r, n_theta, apply_fixes, (cplx*)H, ldh);
+}
+
 int mspde_zpotrf_upper(void* stream, void* A, int lda, int n, void* winv, int* info_dev) {
     return potrf_upper((cudaStream_t)stream, (cplx*)A, lda, n, (cplx*)winv, info_dev);
 }

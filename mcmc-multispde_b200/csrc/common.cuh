@@ -79,4 +79,8 @@ int zgemm_tn(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, con
 int zgemm_tn_splitk(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, const cplx* A, int lda,
                     const cplx* B, int ldb, double beta, cplx* C, int ldc, cplx* part, int nsplit);
 
+// tomography.cu
+int tomography_H(cudaStream_t st, int M, int N, const double* r, const double* theta, const int* ix, const int* iy, int n_r,
+                 int n_theta, int apply_fixes, cplx* H, int ldh);
+
 }  // namespace mspde

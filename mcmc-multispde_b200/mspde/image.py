@@ -219,11 +219,33 @@ class Sinogram(TwoDMeasurement):
             H[b * n_r:(b + 1) * n_r, :] = np.roll(H[b * n_r:(b + 1) * n_r, :], 1, axis=0)
         return H
 
+    def get_measurement_matrix_device(self, ix, iy, device, apply_fixes=True):
+        """Same matrix built on the GPU by mspde_tomography_H: returns an M x N complex128 torch tensor."""
+        import ctypes
+        from . import _ffi
+        shifted = self.theta + self.theta[1]
+        tg, rg = np.meshgrid(shifted * np.float64(util.PI) / 180.0, self.r)
+        rv = torch.as_tensor(np.ascontiguousarray(rg.ravel(ORDER))).to(device)
+        tv = torch.as_tensor(np.ascontiguousarray(tg.ravel(ORDER))).to(device)
+        ixd = torch.as_tensor(np.ascontiguousarray(ix, dtype=np.int32)).to(device)
+        iyd = torch.as_tensor(np.ascontiguousarray(iy, dtype=np.int32)).to(device)
+        M, N = rv.numel(), ixd.numel()
+        ld = (N + 7) // 8 * 8
+        H = torch.zeros((M, ld), dtype=CDTYPE, device=device)[:, :N]
+        with torch.cuda.device(device):
+            _ffi.check(_ffi.lib().mspde_tomography_H(_ffi.current_stream(), M, N, _ffi.ptr(rv), _ffi.ptr(tv), _ffi.ptr(ixd),
+                                                     _ffi.ptr(iyd), self.n_r, self.n_theta, int(bool(apply_fixes)), _ffi.ptr(H),
+                                                     H.stride(0)), "tomography_H")
+        return H
+
     def synthesize(self, H0, fourier: FourierAnalysis_2D):
         """Synthetic stand-in for set_theta (398-404): sinogram = Re(H0 v_true) + stdev * N(0,1)."""
         v_half = fourier.rfft2(torch.as_tensor(self.target_image)).numpy()
         v_true = util.symmetrize_2D(v_half).ravel(ORDER)
-        pure = (H0 @ v_true).real
+        if isinstance(H0, torch.Tensor):
+            pure = (H0 @ torch.as_tensor(v_true).to(H0.device)).real.cpu().numpy()
+        else:
+            pure = (H0 @ v_true).real
         self.pure_sinogram = pure.reshape(self.n_r, self.n_theta, order=ORDER)
         self.sinogram = self.pure_sinogram + self.stdev * self.rng.standard_normal(self.pure_sinogram.shape)
         self.y = self.sinogram.ravel(ORDER) / self.stdev                            # 402
@@ -253,14 +275,18 @@ class pCN:
         self.epsilon = 0
         self.cholesky_stabilizer = 0.0
         N = f.basis_number_2D_sym
-        if H0 is None:                                                              # create_H_matrix, 496-508
-            H0 = measurement.get_measurement_matrix(f.ix.ravel(ORDER), f.iy.ravel(ORDER))
+        dev = torch.device("cuda", device)
+        if H0 is None:                                                              # create_H_matrix, 496-508 (on the device)
+            H0 = measurement.get_measurement_matrix_device(f.ix.ravel(ORDER), f.iy.ravel(ORDER), dev)
         if getattr(measurement, "sinogram", 1) is None:
             measurement.synthesize(H0, f)
         M = H0.shape[0]
         self.ctx = MspdeContext(f.basis_number, f.extended_basis_number, M, n_layers, device=device)
         ctx = self.ctx
-        H0d = ctx.new_matrix(M, N); H0d.copy_(ctx.to_dev(H0, CDTYPE))
+        if isinstance(H0, torch.Tensor) and H0.is_cuda and H0.stride(0) % 8 == 0:
+            H0d = H0
+        else:
+            H0d = ctx.new_matrix(M, N); H0d.copy_(ctx.to_dev(H0, CDTYPE))
         t2 = ctx.gemm_tn(H0d, H0d, conjA=True)                                      # H^H H on the DMMA pipe (505)
         HtH0 = 0.5 * (t2 + t2.conj().transpose(0, 1))                               # 506
         self.H = H0d / self.measurement.stdev                                       # 437

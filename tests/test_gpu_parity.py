@@ -111,6 +111,29 @@ def test_potrf_reports_not_positive_definite(lib):
         _ffi.check(int(info[0]), "zpotrf")
 
 
+def test_tomography_kernel_vs_reference_kernel_golden(golden_dir, lib):
+    """mspde_tomography_H without post-fixes against the reference's own kernel body output (golden), and with them
+    against the oracle's closed form."""
+    from mspde import _ffi
+    from mspde import image as im
+    g = np.load(os.path.join(golden_dir, "ref_H_tomography.npz"))
+    n, n_ext, n_theta = int(g["n"]), int(g["n_ext"]), int(g["n_theta"])
+    ft = o.FourierTables(n, n_ext)
+    sino = im.Sinogram("none.png", target_size=ft.m, n_theta=n_theta, stdev=0.2)
+    dev = torch.device("cuda", 0)
+    H_raw = sino.get_measurement_matrix_device(ft.ix.ravel("F"), ft.iy.ravel("F"), dev, apply_fixes=False).cpu().numpy()
+    assert np.abs(H_raw - g["H_kernel"]).max() < 1e-14
+    H_fix = sino.get_measurement_matrix_device(ft.ix.ravel("F"), ft.iy.ravel("F"), dev, apply_fixes=True).cpu().numpy()
+    assert np.abs(H_fix - o.tomography_H(ft, n_theta)).max() < 1e-14
+    assert np.abs(H_fix - sino.get_measurement_matrix(ft.ix.ravel("F"), ft.iy.ravel("F"))).max() < 1e-14
+    # config-1 geometry against the numpy closed form (relative 1e-12 on entries of O(1))
+    ft2 = o.FourierTables(16, 64)
+    s2 = im.Sinogram("none.png", target_size=ft2.m, n_theta=45, stdev=0.2)
+    Hd = s2.get_measurement_matrix_device(ft2.ix.ravel("F"), ft2.iy.ravel("F"), dev).cpu().numpy()
+    Ho = o.tomography_H(ft2, 45)
+    assert np.abs(Hd - Ho).max() < 1e-12 * np.abs(Ho).max()
+
+
 # ------------------------------------------------------------------------------------------------ assembly
 @pytest.fixture(scope="module")
 def toy():
