@@ -51,6 +51,10 @@ int mspde_construct_L(mspde_ctx* ctx, const void* u_sym, double sqrt_beta, void*
 /* a9: pCN._log_ratio (619-662, default branch); out3 (device) = {Phi, 0.5*||y@C||^2, sum log diag C}. */
 int mspde_phi(mspde_ctx* ctx, const void* L, int ldl, double* out3_dev);
 
+/* Same Phi through the determinant lemma (algorithm note ii): no M-sized work.  Opt-in; results agree with
+ * mspde_phi to rounding (validated at 1e-10 in tests); reported separately from the reference-faithful path. */
+int mspde_phi_fast(mspde_ctx* ctx, const void* L, int ldl, double* out3_dev);
+
 /* a5 + a8: cp.linalg.solve(L, w) (561, 681, 755, 785) and Lmatrix_2D.logDet (268-276; patch/norms.py:236-293).
  * x (N) <- L^-1 rhs; logabsdet_dev (device double, may be NULL) <- log|det L| = sum log|diag| of the factor.
  * L is not modified (it is copied into the workspace). */
@@ -84,7 +88,8 @@ typedef struct {
     double log_u;                   /* log of the accept uniform */
 } mspde_step_noise;
 
-enum { MSPDE_STEP_CACHE_PHI_CUR = 1, MSPDE_STEP_SKIP_GIBBS = 2, MSPDE_STEP_SERIAL = 4 /* one stream, no task overlap */ };
+enum { MSPDE_STEP_CACHE_PHI_CUR = 1, MSPDE_STEP_SKIP_GIBBS = 2, MSPDE_STEP_SERIAL = 4 /* one stream, no task overlap */,
+       MSPDE_STEP_FAST_PHI = 8 /* determinant-lemma Phi (mspde_phi_fast) for both evaluations */ };
 
 /* out_dev (device, 4 doubles) <- {accepted (0/1), logRatio, Phi_cur, Phi_new}; record_dev (optional) <-
  * n_layers x n_ravel current half samples (Layer.record_sample, 792-795). */

@@ -96,6 +96,7 @@ int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n
     CTX_ALLOC(scal, 64);
     CTX_ALLOC(info, 4);
     CTX_ALLOC(vecN, size_t(4) * (N + M));
+    CTX_ALLOC(gvec, N);
     c.ldA = round_up(N + 2, 8);
     CTX_ALLOC(QRaug, size_t(M + N) * c.ldA);
     {
@@ -124,6 +125,8 @@ int mspde_ctx_destroy(mspde_ctx* h) {
     if (h->c.s2) cudaStreamDestroy(h->c.s2);
     for (cudaEvent_t e : {h->c.ev_start, h->c.ev_L, h->c.ev_s1, h->c.ev_s2})
         if (e) cudaEventDestroy(e);
+    for (int s = 0; s < 2; ++s)
+        if (h->c.pw[s].A) cudaFree(h->c.pw[s].A);
     for (void* p : h->owned) cudaFree(p);
     delete h;
     return 0;
@@ -141,6 +144,7 @@ int mspde_ctx_set_inputs(mspde_ctx* h, const void* H, int ldH, const void* Hct, 
     c.Hct = (const cplx*)Hct; c.ldHct = ldHct;
     c.HtH = (const cplx*)HtH; c.ldHtH = ldHtH;
     c.y = y; c.D_diag = D_diag; c.stdev_sym = stdev_sym; c.delta = delta;
+    c.g_valid = false;
     return 0;
 }
 
@@ -234,6 +238,12 @@ int mspde_pcn_step(mspde_ctx* h, const mspde_chain* chain, const mspde_step_nois
         return -1;
     }
     return pcn_step(&h->c, chain, noise, flags, out_dev, (cplx*)record_dev);
+}
+
+int mspde_phi_fast(mspde_ctx* h, const void* L, int ldl, double* out3_dev) {
+    int rc = phi_fast_prepare(&h->c, h->c.stream);
+    if (rc) return rc;
+    return phi_eval_fast(&h->c, h->c.stream, h->c.pw[0], (const cplx*)L, ldl, out3_dev);
 }
 
 int mspde_read_info(mspde_ctx* h, int reset) {

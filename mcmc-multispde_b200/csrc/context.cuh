@@ -10,6 +10,7 @@ struct PhiWork {
     cplx* r = nullptr;        // N x ldN
     cplx* X = nullptr;        // N x ldM   Ht = c^-1 H^H
     cplx* Q = nullptr;        // M x ldM
+    cplx* A = nullptr;        // N x ldN   L^H L + delta I (fast Phi formulation only; allocated on first use)
     cplx* winv = nullptr;     // inverses of 64-blocks, sized for max(N, M)
     double* rowsq = nullptr;  // M
     double* rowlog = nullptr; // M
@@ -54,6 +55,8 @@ struct Ctx {
     int ldA = 0;
     void* qr_work = nullptr;
     cplx* vecN = nullptr;     // scratch vectors (4 x (N+M))
+    cplx* gvec = nullptr;     // H^H y (fast Phi formulation)
+    bool g_valid = false;
 
     // side streams for the independent heavy tasks of one step (Phi(L_current), Gibbs QR) and their events
     cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr;   // main chain (highest priority), Phi(current), Gibbs
@@ -70,6 +73,8 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
 int field_coeffs(Ctx* c, const cplx* u_sym, cplx* tp_out, cplx* tm_out);
 int assemble_L(Ctx* c, const cplx* tp, const cplx* tm, double sqrt_beta, cplx* L, int ldl);
 // phi.cu
-int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3, bool serial = false);   // out3 (device): phi, quad, logdet
+int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3, bool serial = false);
+int phi_fast_prepare(Ctx* c, cudaStream_t st);
+int phi_eval_fast(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3);   // out3 (device): phi, quad, logdet
 
 }  // namespace mspde

@@ -158,6 +158,10 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
         ~StreamGuard() { c->stream = saved; }
     } guard{c, caller};
     cudaStream_t s1 = serial ? st : c->s1, s2 = serial ? st : c->s2;
+    if (flags & MSPDE_STEP_FAST_PHI) {
+        int rc0 = phi_fast_prepare(c, caller);
+        if (rc0) return rc0;
+    }
     if (!serial) {   // internal streams start after everything already queued on the caller's stream
         MSPDE_CUDA(cudaEventRecord(c->ev_start, caller));
         MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_start, 0));
@@ -173,11 +177,13 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
     cplx* v_acc = c->vecN + 2 * size_t(N);
     cplx* v_rej = c->vecN + 3 * size_t(N);
     const bool do_gibbs = !(flags & MSPDE_STEP_SKIP_GIBBS);
+    const bool fast = (flags & MSPDE_STEP_FAST_PHI) != 0;
     int rc;
     // ---- stream s1: Phi(L_current) only depends on the previous step (image_cupy.py:567-568)
     const bool cached = (flags & MSPDE_STEP_CACHE_PHI_CUR) && ch->phi_cur_valid;
     if (!cached) {
-        rc = phi_eval(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3, serial);
+        rc = fast ? phi_eval_fast(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3)
+                  : phi_eval(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3, serial);
         if (rc) return rc;
         if (!serial) MSPDE_CUDA(cudaEventRecord(c->ev_s1, s1));
     }
@@ -231,7 +237,8 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
         MSPDE_LAUNCH_CHECK();
     }
     // ---- main stream: Phi(L_latest) (571), then join
-    rc = phi_eval(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3, serial);
+    rc = fast ? phi_eval_fast(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3)
+              : phi_eval(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3, serial);
     if (rc) return rc;
     if (!serial) {
         if (!cached) MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_s1, 0));

@@ -77,7 +77,99 @@ __global__ void __launch_bounds__(1024) phi_reduce_kernel(const double* __restri
     }
 }
 
+// g = H^H y helper input: y as a complex column
+__global__ void real_to_cplx_kernel(const double* __restrict__ y, cplx* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(y[i], 0.0);
+}
+
+// A = G + delta I (upper), r = G + HtH + delta I (upper) from one Gram matrix G = L^H L stored in r
+__global__ void split_gram_kernel(cplx* __restrict__ r, int ldr, const cplx* __restrict__ HtH, int ldh, double delta,
+                                  cplx* __restrict__ A, int lda, int N) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= N || j < i) return;
+    cplx g = r[size_t(i) * ldr + j];
+    if (i == j) g.x += delta;
+    A[size_t(i) * lda + j] = g;
+    const cplx h = HtH[size_t(i) * ldh + j];
+    r[size_t(i) * ldr + j] = make_double2(g.x + h.x, g.y + h.y);
+}
+
+// out3 = {0.5*(ynorm2 - ||z||^2) + sum log diag(Ur) - sum log diag(Ua), 0.5*(ynorm2 - ||z||^2), -(sum log Ur - sum log Ua)}
+__global__ void __launch_bounds__(1024) phi_fast_reduce_kernel(const cplx* __restrict__ Ur, int ldr, const cplx* __restrict__ Ua,
+                                                               int lda, const cplx* __restrict__ z, const double* __restrict__ y,
+                                                               int N, int M, double* __restrict__ out3) {
+    __shared__ double s1[1024], s2[1024], s3[1024];
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const cplx zi = z[i];
+        a += zi.x * zi.x + zi.y * zi.y;
+        b += log(Ur[size_t(i) * ldr + i].x) - log(Ua[size_t(i) * lda + i].x);
+    }
+    for (int i = threadIdx.x; i < M; i += 1024) c += y[i] * y[i];
+    s1[threadIdx.x] = a; s2[threadIdx.x] = b; s3[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 512; o; o >>= 1) {
+        if (threadIdx.x < o) {
+            s1[threadIdx.x] += s1[threadIdx.x + o];
+            s2[threadIdx.x] += s2[threadIdx.x + o];
+            s3[threadIdx.x] += s3[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double quad = 0.5 * (s3[0] - s1[0]);
+        out3[0] = quad + s2[0];
+        out3[1] = quad;
+        out3[2] = -s2[0];
+    }
+}
+
 }  // namespace
+
+// Results-preserving reformulation of Phi (SURVEY 8d note ii), OPT-IN and reported separately from the reference-faithful
+// Woodbury path:  y^T Q_inv y = ||y||^2 - ||U_r^-H H^H y||^2  and, by the matrix determinant lemma,
+// -sum log diag C = 1/2 log det(I + H A^-1 H^H) = sum log diag U_r - sum log diag U_A,  A = L^H L + delta I = U_A^H U_A,
+// r = A + HtH = U_r^H U_r.  No M-sized product or factorisation is formed: 4N^3 + 2*(4/3)N^3 flops instead of F_Phi.
+int phi_fast_prepare(Ctx* c, cudaStream_t st) {
+    const int N = c->N, M = c->M;
+    for (int s = 0; s < 2; ++s)
+        if (!c->pw[s].A) MSPDE_CUDA(cudaMalloc((void**)&c->pw[s].A, size_t(N) * c->ldN * sizeof(cplx)));   // freed with the context
+    if (!c->g_valid) {          // g = H^H y, once per set of inputs
+        real_to_cplx_kernel<<<(M + 255) / 256, 256, 0, st>>>(c->y, c->pw[0].Q, M);
+        MSPDE_LAUNCH_CHECK();
+        int rc0 = zgemm_tn(st, true, N, 1, M, 1.0, c->H, c->ldH, c->pw[0].Q, 1, 0.0, c->gvec, 1, GEMM_FULL);
+        if (rc0) return rc0;
+        c->g_valid = true;
+    }
+    return 0;
+}
+
+int phi_eval_fast(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3) {
+    const int N = c->N, M = c->M;
+    if (!w.A || !c->g_valid) {
+        set_error("phi_eval_fast: phi_fast_prepare was not called");
+        return -1;
+    }
+    cplx* A = w.A;
+    cplx* z = w.Q;              // first N entries of the Q buffer
+    MSPDE_CUDA(cudaMemsetAsync(w.r, 0, size_t(N) * c->ldN * sizeof(cplx), st));
+    int rc = zgemm_tn(st, true, N, N, N, 1.0, L, ldl, L, ldl, 0.0, w.r, c->ldN, GEMM_UPPER);
+    if (rc) return rc;
+    split_gram_kernel<<<dim3((N + 255) / 256, N), 256, 0, st>>>(w.r, c->ldN, c->HtH, c->ldHtH, c->delta, A, c->ldN, N);
+    MSPDE_LAUNCH_CHECK();
+    rc = potrf_upper(st, A, c->ldN, N, w.winv, c->info, nullptr);
+    if (rc) return rc;
+    rc = potrf_upper(st, w.r, c->ldN, N, w.winv, c->info, nullptr);
+    if (rc) return rc;
+    MSPDE_CUDA(cudaMemcpyAsync(z, c->gvec, size_t(N) * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    rc = trsm_uh(st, w.r, c->ldN, w.winv, N, z, 1, 1);
+    if (rc) return rc;
+    phi_fast_reduce_kernel<<<1, 1024, 0, st>>>(w.r, c->ldN, A, c->ldN, z, c->y, N, M, out3);
+    MSPDE_LAUNCH_CHECK();
+    return 0;
+}
 
 int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3, bool serial) {
     const int N = c->N, M = c->M;

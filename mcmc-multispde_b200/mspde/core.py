@@ -16,6 +16,7 @@ CDTYPE = torch.complex128
 STEP_CACHE_PHI_CUR = 1
 STEP_SKIP_GIBBS = 2
 STEP_SERIAL = 4
+STEP_FAST_PHI = 8
 
 
 class _Chain(ctypes.Structure):
@@ -149,10 +150,11 @@ class MspdeContext:
                                               L.stride(0)), "construct_L")
         return L
 
-    def phi(self, L, parts: bool = False):
-        """Phi(L) of pCN._log_ratio; synchronises to return Python floats."""
+    def phi(self, L, parts: bool = False, fast: bool = False):
+        """Phi(L) of pCN._log_ratio; synchronises to return Python floats.  fast=True: determinant-lemma form."""
         self._sync_stream()
-        _ffi.check(self.lib.mspde_phi(self._h, _ffi.ptr(L), L.stride(0), _ffi.ptr(self.scal)), "phi")
+        fn = self.lib.mspde_phi_fast if fast else self.lib.mspde_phi
+        _ffi.check(fn(self._h, _ffi.ptr(L), L.stride(0), _ffi.ptr(self.scal)), "phi")
         self.check_info("phi (Cholesky)")
         v = self.scal[:3].cpu().numpy()
         return (float(v[0]), float(v[1]), float(v[2])) if parts else float(v[0])

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import util
-from .core import CDTYPE, ChainBuffers, MspdeContext, STEP_CACHE_PHI_CUR, STEP_SKIP_GIBBS
+from .core import CDTYPE, ChainBuffers, MspdeContext, STEP_CACHE_PHI_CUR, STEP_FAST_PHI, STEP_SKIP_GIBBS
 
 ORDER = util.ORDER
 
@@ -306,6 +306,7 @@ class pCN:
         self.use_naive_logRatio_implementation = False
         self.cache_phi_current = False      # results-preserving shortcut (SURVEY 8d note i); off = reference-faithful
         self.skip_gibbs = False
+        self.fast_phi = False               # determinant-lemma Phi (SURVEY 8d note ii); off = reference-faithful Woodbury
         self.noise_source = None            # object with draw_iteration() -> dict (injected noise), else device RNG
         self._inputs_set = False
         self._uploaded = False
@@ -361,7 +362,7 @@ class pCN:
         self._ensure_inputs()
         if self.use_naive_logRatio_implementation:
             raise NotImplementedError("naive Phi variant (644-657) is a SURVEY 8(f2) item, not built yet")
-        return self.ctx.phi(L)
+        return self.ctx.phi(L, fast=self.fast_phi)
 
     # -- one iteration (553-617) ---------------------------------------------------------------------------
     def _bind(self, Layers):
@@ -405,7 +406,8 @@ class pCN:
         self._ensure_inputs(Layers[0].stdev_sym_host)
         cb = self._bind(Layers)
         w_half, log_u, w_last, e = noise if noise is not None else self._draw_noise()
-        flags = (STEP_CACHE_PHI_CUR if self.cache_phi_current else 0) | (STEP_SKIP_GIBBS if self.skip_gibbs else 0)
+        flags = ((STEP_CACHE_PHI_CUR if self.cache_phi_current else 0) | (STEP_SKIP_GIBBS if self.skip_gibbs else 0)
+                 | (STEP_FAST_PHI if self.fast_phi else 0))
         do_record = (self.record_count % self.record_skip) == 0
         rec = self._record_buffer(Layers) if do_record else None
         self.ctx.pcn_step(cb, w_half, log_u, w_last, e, flags=flags, record=rec, out=self._out)

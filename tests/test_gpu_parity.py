@@ -207,6 +207,24 @@ def test_phi_solve_lstsq_vs_oracle(toy):
     assert rel(xg.cpu(), o.lstsq_qr(a, b)) < RTOL
 
 
+def test_fast_phi_matches_woodbury(toy, full):
+    """Determinant-lemma Phi (opt-in) against the oracle at toy size and against the Woodbury GPU path at full size."""
+    hp, pb, pt, ns, st, ctx = toy
+    N = pb["ft"].N
+    for k in (1, 2):
+        L = st.L_cur[k]
+        po, parts = o.phi_woodbury(L, pb["H"], pb["HtH"], pb["y"], pb["delta"], return_parts=True)
+        Ld = ctx.new_matrix(N, N); Ld.copy_(ctx.to_dev(L))
+        pf = ctx.phi(Ld, parts=True, fast=True)
+        assert abs(pf[0] - po) <= RTOL * abs(po)
+        assert abs(pf[1] - parts["quad"]) <= RTOL * abs(parts["quad"])
+    c2 = full.pcn.ctx
+    L = full.Layers[2].LMat.current_L
+    a = c2.phi(L, parts=True)
+    b = c2.phi(L, parts=True, fast=True)
+    assert abs(a[0] - b[0]) <= RTOL * abs(a[0]), (a, b)
+
+
 def _load_chain(ctx, st):
     from mspde.core import ChainBuffers
     K = len(st.noise_cur)
@@ -219,10 +237,12 @@ def _load_chain(ctx, st):
     return cb
 
 
-@pytest.mark.parametrize("n,n_theta,steps,cache", [(4, 8, 6, False), (4, 8, 6, True), (8, 24, 4, False), (3, 12, 5, False)])
+@pytest.mark.parametrize("n,n_theta,steps,cache", [(4, 8, 6, False), (4, 8, 6, True), (8, 24, 4, False), (3, 12, 5, False),
+                                                   (4, 8, 6, "fast"), (8, 24, 4, "serial")])
 def test_pcn_chain_vs_oracle(n, n_theta, steps, cache):
     """Whole iterations with injected noise: accept decisions identical, Phi / samples within 1e-10."""
-    from mspde.core import MspdeContext, STEP_CACHE_PHI_CUR
+    from mspde.core import MspdeContext, STEP_CACHE_PHI_CUR, STEP_FAST_PHI, STEP_SERIAL
+    flag = {False: 0, True: STEP_CACHE_PHI_CUR, "fast": STEP_FAST_PHI, "serial": STEP_SERIAL}[cache]
     hp = o.Hyper(n_layers=3, n=n, n_ext=64, n_theta=n_theta)
     pb = o.synthetic_problem(hp)
     ft, H, HtH, y, delta = pb["ft"], pb["H"], pb["HtH"], pb["y"], pb["delta"]
@@ -240,7 +260,7 @@ def test_pcn_chain_vs_oracle(n, n_theta, steps, cache):
         d = o.one_step(st, ft, H, HtH, y, delta, nz)
         cb.set_step(st.beta)
         out = ctx.pcn_step(cb, [ctx.to_dev(w) for w in nz["w_half"]], nz["log_u"], ctx.to_dev(nz["w_last"]), ctx.to_dev(nz["e"]),
-                           flags=STEP_CACHE_PHI_CUR if cache else 0, record=rec)
+                           flags=flag, record=rec)
         ctx.check_info("step")
         g = out.cpu().numpy()
         min_margin = min(min_margin, abs(d["log_ratio"] - d["log_u"]))
