@@ -303,6 +303,9 @@ class pCN:
         self.record_count = 0
         self.max_record_history = 1000000
         self.use_beta_adaptation = False
+        self.pcn_step_sqrtBetas = 5e-1                                              # 467
+        self.pcn_step_sqrtBetas_Z = math.sqrt(1 - self.pcn_step_sqrtBetas)          # 468 (sic: no square, as in the reference)
+        self.stdev_sqrtBetas = np.ones(n_layers)                                    # 469
         self.use_naive_logRatio_implementation = False
         self.cache_phi_current = False      # results-preserving shortcut (SURVEY 8d note i); off = reference-faithful
         self.skip_gibbs = False
@@ -423,7 +426,60 @@ class pCN:
                 l.record_sample(self._rec_host[k].numpy())
                 l.record_sqrt_beta()
         self.record_count += 1
-        return accepted, 0
+        accepted_SqrtBeta = self.one_step_for_sqrtBetas(Layers) if self.use_beta_adaptation else 0      # 604-607
+        return accepted, accepted_SqrtBeta
+
+    # -- optional hyper-parameter move (666-710) ------------------------------------------------------------
+    def one_step_for_sqrtBetas(self, Layers, noise=None):
+        """pCN.one_step_for_sqrtBetas with the reference's semantics (see the oracle restatement for the quirks).
+        Composed from the C-ABI pieces (construct_L, solve, gibbs_lstsq, phi); off by default like the reference
+        (use_beta_adaptation = False, image_cupy.py:470).  noise: dict(z, e, log_u) to inject, else device RNG."""
+        ctx, K = self.ctx, self.n_layers
+        self._ensure_inputs(Layers[0].stdev_sym_host)
+        if noise is None:
+            g = self.random_gen.gen
+            noise = dict(z=torch.randn(K, dtype=torch.float64, device=ctx.device, generator=g).cpu().numpy(),
+                         e=torch.randn(ctx.M, dtype=torch.float64, device=ctx.device, generator=g),
+                         log_u=math.log(float(torch.rand(1, dtype=torch.float64, device=ctx.device, generator=g).item())))
+        s = self.pcn_step_sqrtBetas
+        z = np.asarray(self.stdev_sqrtBetas) * np.asarray(noise["z"])                                  # 668
+        e = ctx.to_dev(noise["e"], torch.float64)
+        prop = np.zeros(K)
+        stdev_sym_temp = None
+        for i in range(K):
+            prop[i] = math.exp(math.sqrt(1 - s ** 2) * math.log(Layers[i].sqrt_beta) + s * z[i])       # 673-674
+            if i == 0:
+                stdev_sym_temp = (prop[0] / Layers[0].sqrt_beta) * Layers[0].stdev_sym_host            # 676
+                Layers[0]._u_new.copy_(ctx.to_dev(stdev_sym_temp, torch.float64) * Layers[0]._noise_cur)   # 677
+            else:
+                Layers[i]._ensure_two_L_buffers()
+                Layers[i].LMat.construct_from_with_sqrt_beta(Layers[i - 1]._u_new, prop[i])            # 679
+                if i < K - 1:
+                    Layers[i]._u_new.copy_(ctx.solve(Layers[i].LMat.latest_computed_L, Layers[i]._noise_cur))   # 681
+                else:
+                    wBar = torch.cat((e.to(CDTYPE), Layers[-1]._noise_cur))                            # 683-685
+                    rhs = self.yBar.to(CDTYPE) - wBar
+                    Layers[-1]._u_new.copy_(ctx.gibbs_lstsq(Layers[-1].LMat.latest_computed_L, rhs))   # 686-688
+        phi_cur = self._log_ratio(Layers[-1].LMat.current_L)                                           # 692-693
+        L = Layers[-1].LMat.construct_from(Layers[-2]._u_new)                                          # 695 (LMat.sqrt_beta)
+        phi_new = self._log_ratio(L)                                                                   # 696
+        log_ratio = phi_cur - phi_new
+        accepted = int(log_ratio > float(noise["log_u"]))                                              # 699
+        if accepted:
+            for i in range(K):                                                                         # 703-708
+                Layers[i].sqrt_beta = float(prop[i])
+                if not Layers[i].is_stationary:
+                    Layers[i].LMat.set_current_L_to_latest()
+                    Layers[i].LMat.latest_computed_L = Layers[i]._clone_padded(Layers[i].LMat.current_L)
+                else:
+                    Layers[i].stdev_sym = stdev_sym_temp
+            if self._chain is not None:
+                self._chain.sqrt_betas = [float(l.sqrt_beta) for l in Layers]
+                import ctypes
+                self._chain._sb = (ctypes.c_double * K)(*self._chain.sqrt_betas)
+                self._chain.phi_cur_valid = 0
+        self.last_sqrt_beta_step = dict(accepted=accepted, log_ratio=log_ratio, phi_cur=phi_cur, phi_new=phi_new, prop=prop)
+        return accepted
 
     def _record_buffer(self, Layers):
         if getattr(self, "_rec", None) is None:

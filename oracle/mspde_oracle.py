@@ -463,6 +463,46 @@ def one_step(st: ChainState, ft: FourierTables, H, HtH, y, delta, noise: dict, t
                 log_u=float(noise["log_u"]))
 
 
+def one_step_for_sqrt_betas(st: ChainState, ft: FourierTables, H, HtH, y, delta, noise: dict, lmat_sqrt_betas: list,
+                            pcn_step_sqrt_betas: float = 0.5, stdev_sqrt_betas=None):
+    """Optional hyper-parameter move ``pCN.one_step_for_sqrtBetas`` (mcmc/image_cupy.py:666-710), restated with its quirks:
+    line 673 uses ``sqrt(1 - s^2)`` (not the stored ``pcn_step_sqrtBetas_Z``); line 695 re-assembles the last layer with the
+    Lmatrix's own ``sqrt_beta`` (``lmat_sqrt_betas``: fixed at construction, never updated by an acceptance); an acceptance
+    (699-708) updates ``sqrt_beta``/``current_L``/``stdev_sym`` but NOT the current samples.
+    noise: dict(z = n_layers normals, e = M normals, log_u)."""
+    K, N = len(st.noise_cur), ft.N
+    s = pcn_step_sqrt_betas
+    sd = np.ones(K) if stdev_sqrt_betas is None else np.asarray(stdev_sqrt_betas)
+    z = sd * noise["z"]                                                                            # 668
+    prop = np.zeros(K)
+    stdev_sym_temp = None
+    for i in range(K):
+        prop[i] = np.exp(np.sqrt(1 - s ** 2) * np.log(st.sqrt_betas[i]) + s * z[i])                # 673-674
+        if i == 0:
+            stdev_sym_temp = (prop[0] / st.sqrt_betas[0]) * st.stdev_sym                           # 676
+            st.u_new_sym[0] = stdev_sym_temp * st.noise_cur[0]                                     # 677
+        else:
+            st.L_latest[i] = assemble_L(st.u_new_sym[i - 1], prop[i], ft)                          # 679
+            if i < K - 1:
+                st.u_new_sym[i] = np.linalg.solve(st.L_latest[i], st.noise_cur[i])                 # 681
+            else:
+                wBar = np.concatenate((noise["e"].astype(np.complex128), st.noise_cur[K - 1]))     # 683-685
+                yBar = np.concatenate((y, np.zeros(N)))
+                st.u_new_sym[K - 1] = lstsq_qr(np.vstack((H, st.L_latest[K - 1])), yBar - wBar)    # 686-688
+    phi_cur = phi_woodbury(st.L_cur[K - 1], H, HtH, y, delta)                                      # 692-693
+    st.L_latest[K - 1] = assemble_L(st.u_new_sym[K - 2], lmat_sqrt_betas[K - 1], ft)               # 695 (LMat's own sqrt_beta)
+    phi_new = phi_woodbury(st.L_latest[K - 1], H, HtH, y, delta)                                   # 696
+    log_ratio = phi_cur - phi_new
+    accepted = bool(log_ratio > noise["log_u"])                                                    # 699
+    if accepted:
+        for i in range(K):                                                                         # 703-708
+            st.sqrt_betas[i] = float(prop[i])
+            if i >= 1:
+                st.L_cur[i] = st.L_latest[i]
+        st.stdev_sym = stdev_sym_temp
+    return dict(accepted=accepted, log_ratio=float(log_ratio), phi_cur=float(phi_cur), phi_new=float(phi_new), prop=prop)
+
+
 def adapt_step(st: ChainState, hp: Hyper):
     """``Simulation.run`` step adaptation (mcmc/image_cupy.py:975-982) -> ``pCN.adapt_step/set_step`` (528-540):
     cumulative acceptance rate; update ignored outside (1e-7, 1)."""

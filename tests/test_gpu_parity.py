@@ -277,6 +277,47 @@ def test_pcn_chain_vs_oracle(n, n_theta, steps, cache):
     assert min_margin > 1e-6      # no accept decision was a near-tie, so the identical decisions are meaningful
 
 
+def test_sqrt_beta_move_vs_oracle():
+    """Optional hyper-parameter move (image_cupy.py:666-710) through the host mirror vs the oracle restatement."""
+    from mspde import image as im
+    hp = o.Hyper(n_layers=3, n=4, n_ext=64, n_theta=8, beta=0.5)
+    sim = im.Simulation(n_layers=3, n_samples=4, n=4, n_extended=64, beta=0.5, kappa=5e9, sigma_0=4e7, sigma_v=3.2e4,
+                        sigma_scaling=0.4, meas_std=0.2, evaluation_interval=2, printProgress=False, seed=3, burn_percentage=25.0,
+                        enable_step_adaptation=True, pcn_variant="dunlop", phantom_name="shepp.png", n_theta=8)
+    sim.pcn.set_chol_epsilon(1e-6)
+    pcn, ctx, Layers = sim.pcn, sim.pcn.ctx, sim.Layers
+    pcn._ensure_inputs(Layers[0].stdev_sym_host)
+    ft = o.FourierTables(4, 64)
+    H, HtH, y = ctx.H.cpu().numpy(), ctx.HtH.cpu().numpy(), ctx.y.cpu().numpy()
+    K = 3
+    st = o.ChainState(beta=0.5, betaZ=float(np.sqrt(0.75)), sqrt_betas=[float(l.sqrt_beta) for l in Layers],
+                      stdev_sym=Layers[0].stdev_sym_host.copy(), noise_cur=[l._noise_cur.cpu().numpy() for l in Layers],
+                      noise_new=[l._noise_new.cpu().numpy() for l in Layers], u_cur_sym=[l._u_cur.cpu().numpy() for l in Layers],
+                      u_new_sym=[l._u_new.cpu().numpy() for l in Layers],
+                      L_cur=[None] + [l.LMat.current_L.cpu().numpy() for l in Layers[1:]],
+                      L_latest=[None] + [l.LMat.latest_computed_L.cpu().numpy() for l in Layers[1:]])
+    lmat_sb = [float(l.LMat.sqrt_beta) for l in Layers]
+    rng = np.random.default_rng(5)
+    for rep, log_u in enumerate([-1e9, 1e9, -1e9]):               # forced accept, forced reject, accept again
+        nz = dict(z=rng.standard_normal(K), e=rng.standard_normal(ctx.M), log_u=log_u)
+        d = o.one_step_for_sqrt_betas(st, ft, H, HtH, y, ctx.delta, nz, lmat_sb)
+        acc = pcn.one_step_for_sqrtBetas(Layers, noise=nz)
+        g = pcn.last_sqrt_beta_step
+        assert acc == int(d["accepted"]) == (1 if log_u < 0 else 0)
+        assert np.allclose(g["prop"], d["prop"], rtol=1e-14)
+        assert abs(g["phi_cur"] - d["phi_cur"]) <= RTOL * abs(d["phi_cur"])
+        assert abs(g["phi_new"] - d["phi_new"]) <= RTOL * abs(d["phi_new"])
+        for k in range(K):
+            assert rel(Layers[k]._u_new.cpu(), st.u_new_sym[k]) < RTOL
+            assert abs(Layers[k].sqrt_beta - st.sqrt_betas[k]) <= 1e-14 * st.sqrt_betas[k]
+        assert rel(Layers[2].LMat.current_L.cpu(), st.L_cur[2]) < RTOL
+        assert rel(Layers[0].stdev_sym_host, st.stdev_sym) < 1e-15
+    # and the regular step still runs afterwards with the updated hyper-parameters
+    pcn.use_beta_adaptation = True
+    a, b = pcn.one_step(Layers)
+    assert a in (0, 1) and b in (0, 1)
+
+
 def test_chain_against_committed_golden(golden_dir, toy):
     """Same toy chain as tests/golden/oracle_chain_n4.npz (generated by oracle/make_golden.py in the build container)."""
     hp, pb, pt, ns_unused, st_unused, ctx = toy
