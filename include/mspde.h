@@ -26,6 +26,8 @@ long long mspde_launch_count(void);   /* kernels launched by the library so far 
 /* Context = sizes + borrowed fixed inputs + library-owned workspace (replaces the managed-memory pool and the
  * temporaries of pCN._log_ratio, mcmc/image_cupy.py:834-835, 634-643). */
 int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n_layers, void* stream);
+enum { MSPDE_CTX_ASSEMBLY_ONLY = 1 };   /* no Phi/QR workspaces: only field synthesis + assembly (distributed path) */
+int mspde_ctx_create_ex(mspde_ctx** out, int device, int n, int n_ext, int M, int n_layers, void* stream, int flags);
 int mspde_ctx_destroy(mspde_ctx* ctx);
 int mspde_ctx_set_stream(mspde_ctx* ctx, void* stream);
 /* H (M x N), H^H (N x M), HtH (N x N), y (M), D_diag (N), stdev_sym (N), delta = chol_epsilon*||HtH||_F
@@ -111,6 +113,13 @@ int mspde_zgemm_tn(void* stream, int conjA, int m, int n, int k, double alpha, c
                    int ldb, double beta, void* C, int ldc, int uplo, void* splitk_ws, int nsplit);
 int mspde_zpotrf_upper(void* stream, void* A, int lda, int n, void* winv, int* info_dev);
 int mspde_ztrsm_uh(void* stream, const void* U, int ldu, const void* winv, int n, void* B, int ldb, int ncols);
+
+/* Helpers of the block-distributed Phi (mspde/dist.py): A[i][i] += v; and, for an upper-trapezoidal row
+ * panel V (nrows x ncols, diagonal at column 0): rowsq[j] = |sum_{i>=j} V[j][i] y[i]|^2, rowlog[j] = log Re V[j][j]
+ * (the pieces of 0.5*||y@C||^2 - sum log diag C, image_cupy.py:643). */
+int mspde_add_diag(void* stream, void* A, int lda, int n, double v);
+int mspde_upper_rows_times_y(void* stream, const void* V, int ldv, int nrows, int ncols, const double* y, double* rowsq,
+                             double* rowlog);
 
 #ifdef __cplusplus
 }

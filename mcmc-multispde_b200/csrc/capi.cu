@@ -44,6 +44,10 @@ const char* mspde_last_error(void) { return get_error(); }
 long long mspde_launch_count(void) { return g_launches; }
 
 int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n_layers, void* stream) {
+    return mspde_ctx_create_ex(out, device, n, n_ext, M, n_layers, stream, 0);
+}
+
+int mspde_ctx_create_ex(mspde_ctx** out, int device, int n, int n_ext, int M, int n_layers, void* stream, int flags) {
     if (!out || n < 2 || n_ext < n || M < 1 || n_layers < 2) {
         set_error("mspde_ctx_create: bad arguments (n=%d n_ext=%d M=%d n_layers=%d)", n, n_ext, M, n_layers);
         return -1;
@@ -64,6 +68,22 @@ int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n
     CTX_ALLOC(G, size_t(2) * m * n);
     CTX_ALLOC(tp, size_t(il) * il);
     CTX_ALLOC(tm, size_t(il) * il);
+    CTX_ALLOC(scal, 64);
+    CTX_ALLOC(info, 4);
+    MSPDE_CUDA(cudaMemset(c.info, 0, 4 * sizeof(int)));
+    MSPDE_CUDA(cudaMemset(c.scal, 0, 64 * sizeof(double)));
+    {
+        std::vector<cplx> w(m);
+        for (int a = 0; a < m; ++a) {
+            const double ang = 2.0 * M_PI * double(a) / double(m);
+            w[a] = make_double2(cos(ang), sin(ang));
+        }
+        MSPDE_CUDA(cudaMemcpy(c.W, w.data(), m * sizeof(cplx), cudaMemcpyHostToDevice));
+    }
+    if (flags & MSPDE_CTX_ASSEMBLY_ONLY) {   // field synthesis + assembly only (block-distributed path keeps its own buffers)
+        *out = h;
+        return 0;
+    }
     for (int s = 0; s < 2; ++s) {
         CTX_ALLOC(pw[s].r, size_t(N) * c.ldN);
         CTX_ALLOC(pw[s].X, size_t(N) * c.ldM);
@@ -93,8 +113,6 @@ int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n
     MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_L, cudaEventDisableTiming));
     MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_s1, cudaEventDisableTiming));
     MSPDE_CUDA(cudaEventCreateWithFlags(&c.ev_s2, cudaEventDisableTiming));
-    CTX_ALLOC(scal, 64);
-    CTX_ALLOC(info, 4);
     CTX_ALLOC(vecN, size_t(4) * (N + M));
     CTX_ALLOC(gvec, N);
     c.ldA = round_up(N + 2, 8);
@@ -105,14 +123,6 @@ int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n
         h->owned.push_back(w);
         c.qr_work = w;
     }
-    MSPDE_CUDA(cudaMemset(c.info, 0, 4 * sizeof(int)));
-    MSPDE_CUDA(cudaMemset(c.scal, 0, 64 * sizeof(double)));
-    std::vector<cplx> w(m);
-    for (int a = 0; a < m; ++a) {
-        const double ang = 2.0 * M_PI * double(a) / double(m);
-        w[a] = make_double2(cos(ang), sin(ang));
-    }
-    MSPDE_CUDA(cudaMemcpy(c.W, w.data(), m * sizeof(cplx), cudaMemcpyHostToDevice));
     *out = h;
     return 0;
 }
@@ -269,6 +279,15 @@ int mspde_zgemm_tn(void* stream, int conjA, int m, int n, int k, double alpha, c
 int mspde_tomography_H(void* stream, int M, int N, const double* r_flat, const double* theta_flat, const int32_t* ix,
                        const int32_t* iy, int n_r, int n_theta, int apply_fixes, void* H, int ldh) {
     return tomography_H((cudaStream_t)stream, M, N, r_flat, theta_flat, ix, iy, n_r, n_theta, apply_fixes, (cplx*)H, ldh);
+}
+
+int mspde_add_diag(void* stream, void* A, int lda, int n, double v) {
+    return add_diag((cudaStream_t)stream, (cplx*)A, lda, n, v);
+}
+
+int mspde_upper_rows_times_y(void* stream, const void* V, int ldv, int nrows, int ncols, const double* y, double* rowsq,
+                             double* rowlog) {
+    return upper_rows_times_y((cudaStream_t)stream, (const cplx*)V, ldv, nrows, ncols, y, rowsq, rowlog);
 }
 
 int mspde_zpotrf_upper(void* stream, void* A, int lda, int n, void* winv, int* info_dev) {

@@ -74,6 +74,9 @@ int field_coeffs(Ctx* c, const cplx* u_sym, cplx* tp_out, cplx* tm_out);
 int assemble_L(Ctx* c, const cplx* tp, const cplx* tm, double sqrt_beta, cplx* L, int ldl);
 // phi.cu
 int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3, bool serial = false);
+int add_diag(cudaStream_t st, cplx* A, int lda, int n, double v);
+int upper_rows_times_y(cudaStream_t st, const cplx* V, int ldv, int nrows, int ncols, const double* y, double* rowsq,
+                       double* rowlog);
 int phi_fast_prepare(Ctx* c, cudaStream_t st);
 int phi_eval_fast(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3);   // out3 (device): phi, quad, logdet
 

@@ -51,6 +51,31 @@ __global__ void __launch_bounds__(256) vy_kernel(const cplx* __restrict__ V, int
     }
 }
 
+__global__ void __launch_bounds__(256) vy_rows_kernel(const cplx* __restrict__ V, int ldv, const double* __restrict__ y,
+                                                      int nrows, int ncols, double* __restrict__ rowsq,
+                                                      double* __restrict__ rowlog) {
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j >= nrows) return;
+    const cplx* row = V + size_t(j) * ldv;
+    double sx = 0.0, sy = 0.0;
+    for (int i = j + lane; i < ncols; i += 32) {
+        const cplx v = row[i];
+        const double yi = y[i];
+        sx = fma(v.x, yi, sx);
+        sy = fma(v.y, yi, sy);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    }
+    if (lane == 0) {
+        rowsq[j] = sx * sx + sy * sy;
+        rowlog[j] = log(row[j].x);
+    }
+}
+
 // deterministic single-block reduction: out = {0.5*sum(rowsq) - sum(rowlog), 0.5*sum(rowsq), sum(rowlog)}
 __global__ void __launch_bounds__(1024) phi_reduce_kernel(const double* __restrict__ rowsq, const double* __restrict__ rowlog,
                                                           int M, double* __restrict__ out3) {
@@ -127,6 +152,20 @@ __global__ void __launch_bounds__(1024) phi_fast_reduce_kernel(const cplx* __res
 }
 
 }  // namespace
+
+// exported helpers for the block-distributed Phi (mspde/dist.py)
+int add_diag(cudaStream_t st, cplx* A, int lda, int n, double v) {
+    add_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(A, lda, n, v);
+    MSPDE_LAUNCH_CHECK();
+    return 0;
+}
+// rows of an upper-trapezoidal panel V (nrows x ncols, diagonal at column 0) times y: rowsq[j] = |sum_{i>=j} V[j][i] y[i]|^2
+int upper_rows_times_y(cudaStream_t st, const cplx* V, int ldv, int nrows, int ncols, const double* y, double* rowsq,
+                       double* rowlog) {
+    vy_rows_kernel<<<(nrows + 7) / 8, 256, 0, st>>>(V, ldv, y, nrows, ncols, rowsq, rowlog);
+    MSPDE_LAUNCH_CHECK();
+    return 0;
+}
 
 // Results-preserving reformulation of Phi (SURVEY 8d note ii), OPT-IN and reported separately from the reference-faithful
 // Woodbury path:  y^T Q_inv y = ||y||^2 - ||U_r^-H H^H y||^2  and, by the matrix determinant lemma,

@@ -47,7 +47,7 @@ def _round_up(x, a):
 
 
 class MspdeContext:
-    def __init__(self, n: int, n_ext: int, M: int, n_layers: int, device: int = 0):
+    def __init__(self, n: int, n_ext: int, M: int, n_layers: int, device: int = 0, assembly_only: bool = False):
         self.lib = _ffi.lib()
         self.device = torch.device("cuda", device)
         self.n, self.n_ext, self.M, self.n_layers = n, n_ext, M, n_layers
@@ -59,8 +59,8 @@ class MspdeContext:
         self.ldM = _round_up(M, 8)
         self._h = ctypes.c_void_p()
         torch.cuda.set_device(self.device)
-        _ffi.check(self.lib.mspde_ctx_create(ctypes.byref(self._h), device, n, n_ext, M, n_layers, _ffi.current_stream()),
-                   "mspde_ctx_create")
+        _ffi.check(self.lib.mspde_ctx_create_ex(ctypes.byref(self._h), device, n, n_ext, M, n_layers, _ffi.current_stream(),
+                                                1 if assembly_only else 0), "mspde_ctx_create")
         self._keep = {}
         self.scal = torch.zeros(16, dtype=torch.float64, device=self.device)
 

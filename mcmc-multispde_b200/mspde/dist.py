@@ -1,0 +1,216 @@
+"""Block-distributed Phi(L) for one chain at the largest basis sizes (BASELINE config 5).
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  The N x N and M x M Hermitian systems of
+pCN._log_ratio (/root/reference/mcmc/image_cupy.py:634-643) are held in a 1-D block-cyclic layout over row blocks
+(row block i of width `nb` lives on rank i mod P, stored row-major, upper part used):
+
+  r = L^H L + HtH + delta I   each rank forms its own row blocks with local DMMA GEMMs (L is replicated: the fused
+                              assembly writes it from the (2n-1)^2 tables in a few ms, no communication)
+  U = chol(r)                 right-looking: the owner factorises the diagonal block and solves its row panel locally,
+                              broadcasts the nb x (n - p nb) panel (ncclBroadcast), every rank updates its own row
+                              blocks below with U12_i^H U12 (zgemm_tn, K = nb)
+  Ht = U^-H H^H               the M right-hand sides are split across ranks (U is complete on every rank after the
+                              panel broadcasts), then all_gather
+  Q_inv = I - Ht^H Ht, V = chol(Q_inv), Phi = 0.5 ||V y||^2 - sum log diag V      same layout, final all_reduce of 2 scalars
+
+Every numerical operation is a libmspde C-ABI call on sub-blocks; torch is used for buffers, copies and NCCL only.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _ffi
+
+CDTYPE = torch.complex128
+c_double = ctypes.c_double
+
+
+def _round_up(x, a):
+    return (x + a - 1) // a * a
+
+
+class BlockRows:
+    """Owned row blocks of an n x n matrix, row-major with a padded leading dimension."""
+
+    def __init__(self, n, nb, world, rank, device):
+        self.n, self.nb, self.world, self.rank = n, nb, world, rank
+        self.nblk = (n + nb - 1) // nb
+        self.owned = [i for i in range(self.nblk) if i % world == rank]
+        self.ld = _round_up(n, 8)
+        self.row0 = {}
+        r = 0
+        for i in self.owned:
+            self.row0[i] = r
+            r += self.rows(i)
+        self.data = torch.zeros((max(r, 1), self.ld), dtype=CDTYPE, device=device)
+
+    def rows(self, i):
+        return min(self.nb, self.n - i * self.nb)
+
+    def block(self, i):
+        """[rows(i), n] view of row block i."""
+        r = self.row0[i]
+        return self.data[r:r + self.rows(i), :self.n]
+
+
+class DistPhi:
+    def __init__(self, N, M, nb=512, device=None):
+        self.lib = _ffi.lib()
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.N, self.M, self.nb = N, M, nb
+        self.info = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.timings = {}
+
+    # ---- thin C-ABI wrappers on strided views ------------------------------------------------------------------
+    def _gemm(self, A, B, C, alpha, beta, upper):
+        k, m = A.shape
+        n = B.shape[1]
+        _ffi.check(self.lib.mspde_zgemm_tn(_ffi.current_stream(), 1, m, n, k, c_double(alpha), _ffi.ptr(A), A.stride(0),
+                                           _ffi.ptr(B), B.stride(0), c_double(beta), _ffi.ptr(C), C.stride(0),
+                                           1 if upper else 0, None, 1), "zgemm_tn")
+
+    def _potrf(self, A, winv):
+        _ffi.check(self.lib.mspde_zpotrf_upper(_ffi.current_stream(), _ffi.ptr(A), A.stride(0), A.shape[0], _ffi.ptr(winv),
+                                               _ffi.ptr(self.info)), "zpotrf")
+
+    def _trsm(self, U, winv, B):
+        _ffi.check(self.lib.mspde_ztrsm_uh(_ffi.current_stream(), _ffi.ptr(U), U.stride(0), _ffi.ptr(winv), U.shape[0],
+                                           _ffi.ptr(B), B.stride(0), B.shape[1]), "ztrsm")
+
+    # ---- building blocks ---------------------------------------------------------------------------------------
+    def gram_rows(self, A, out: BlockRows, alpha, beta):
+        """out[i-rows, i*nb:] = alpha * A[:, i-rows]^H A[:, i*nb:] + beta * out (upper part of every owned row block)."""
+        nb = self.nb
+        for i in out.owned:
+            c0 = i * nb
+            blk = out.block(i)
+            self._gemm(A[:, c0:c0 + out.rows(i)], A[:, c0:], blk[:, c0:], alpha, beta, True)
+
+    def cholesky(self, mat: BlockRows, keep_full=None, winv_all=None, y=None):
+        """In-place distributed upper Cholesky.  keep_full: optional n x n buffer receiving the complete factor (panels are
+        seen by every rank anyway).  winv_all: inverses of the 64-blocks (needed with keep_full for the later solve).
+        y: if given, returns the local partial sums (sum |V y|^2 rows, sum log diag) of the owned panels."""
+        n, nb, P = mat.n, mat.nb, self.world
+        nblk = mat.nblk
+        panel = torch.empty(nb * _round_up(n, 8), dtype=CDTYPE, device=self.device)
+        wblk = (nb // 64) * 64 * 64
+        wbuf = torch.empty(wblk, dtype=CDTYPE, device=self.device)
+        acc = torch.zeros(2, dtype=torch.float64, device=self.device)
+        rowsq = torch.empty(nb, dtype=torch.float64, device=self.device)
+        rowlog = torch.empty(nb, dtype=torch.float64, device=self.device)
+        for p in range(nblk):
+            owner = p % P
+            bp = mat.rows(p)
+            c0 = p * nb
+            w = n - c0
+            pv = panel[: bp * w].view(bp, w)
+            if self.rank == owner:
+                blk = mat.block(p)
+                self._potrf(blk[:, c0:c0 + bp], wbuf)
+                if w > bp:
+                    self._trsm(blk[:, c0:c0 + bp], wbuf, blk[:, c0 + bp:])
+                pv.copy_(blk[:, c0:])
+                if y is not None:
+                    _ffi.check(self.lib.mspde_upper_rows_times_y(_ffi.current_stream(), _ffi.ptr(pv), pv.stride(0), bp, w,
+                                                                 _ffi.ptr(y[c0:]), _ffi.ptr(rowsq), _ffi.ptr(rowlog)), "vy")
+                    acc[0] += rowsq[:bp].sum()
+                    acc[1] += rowlog[:bp].sum()
+            if P > 1:
+                dist.broadcast(torch.view_as_real(pv), src=owner)
+                if winv_all is not None:
+                    dist.broadcast(torch.view_as_real(wbuf), src=owner)
+            if keep_full is not None:
+                keep_full[c0:c0 + bp, c0:] = pv
+            if winv_all is not None:
+                winv_all[p * wblk:(p + 1) * wblk] = wbuf
+            for i in mat.owned:                      # trailing update of the owned row blocks below the panel
+                if i <= p:
+                    continue
+                o = (i - p) * nb
+                bi = mat.rows(i)
+                self._gemm(pv[:, o:o + bi], pv[:, o:], mat.block(i)[:, i * nb:], -1.0, 1.0, True)
+        return acc
+
+    # ---- Phi ---------------------------------------------------------------------------------------------------
+    def setup(self, H, y, delta, HtH_rows: BlockRows | None = None):
+        """H: full M x N (replicated), y: M.  HtH row blocks are formed with the same distributed Gram kernel unless given."""
+        self.H, self.y, self.delta = H, y, float(delta)
+        N, M, nb = self.N, self.M, self.nb
+        if HtH_rows is None:
+            HtH_rows = BlockRows(N, nb, self.world, self.rank, self.device)
+            self.gram_rows(H, HtH_rows, 1.0, 0.0)
+            for i in HtH_rows.owned:               # Hermitian by construction; clear the rounding-level imaginary diagonal
+                d = HtH_rows.block(i)[:, i * nb:].diagonal()
+                d.imag.zero_()
+        self.HtH_rows = HtH_rows
+        self.r = BlockRows(N, nb, self.world, self.rank, self.device)
+        self.Q = BlockRows(M, nb, self.world, self.rank, self.device)
+        self.U = torch.zeros((N, _round_up(N, 8)), dtype=CDTYPE, device=self.device)[:, :N]
+        self.winv = torch.zeros(self.r.nblk * (nb // 64) * 64 * 64, dtype=CDTYPE, device=self.device)
+        self.mc = _round_up((M + self.world - 1) // self.world, 8)          # right-hand sides per rank
+        self.Ht_chunk = torch.zeros((N, self.mc), dtype=CDTYPE, device=self.device)
+        self.Ht_all = torch.zeros((self.world, N, self.mc), dtype=CDTYPE, device=self.device)
+        self.Ht = torch.zeros((N, _round_up(self.mc * self.world, 8)), dtype=CDTYPE, device=self.device)
+        lo = self.rank * self.mc
+        hi = min(M, lo + self.mc)
+        self.Ht_chunk.zero_()
+        if hi > lo:
+            self._Hct_chunk = H[lo:hi, :].conj().transpose(0, 1).contiguous()      # H^H columns of this rank (setup copy)
+        else:
+            self._Hct_chunk = None
+        self._lohi = (lo, hi)
+
+    def phi(self, L):
+        """Phi(L) for the replicated N x N matrix L; collective call, returns a Python float on every rank."""
+        N, M, nb = self.N, self.M, self.nb
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record()
+        # r = HtH + delta I + L^H L on the owned row blocks
+        self.r.data.copy_(self.HtH_rows.data)
+        for i in self.r.owned:
+            blk = self.r.block(i)[:, i * nb:]
+            _ffi.check(self.lib.mspde_add_diag(_ffi.current_stream(), _ffi.ptr(blk), blk.stride(0), blk.shape[0],
+                                               c_double(self.delta)), "add_diag")
+        self.gram_rows(L, self.r, 1.0, 1.0)
+        ev[1].record()
+        self.cholesky(self.r, keep_full=self.U, winv_all=self.winv)
+        ev[2].record()
+        # Ht = U^-H H^H for this rank's right-hand sides, then gather
+        lo, hi = self._lohi
+        if hi > lo:
+            self.Ht_chunk[:, :hi - lo].copy_(self._Hct_chunk)
+            self._trsm(self.U, self.winv, self.Ht_chunk)
+        if self.world > 1:
+            dist.all_gather_into_tensor(torch.view_as_real(self.Ht_all), torch.view_as_real(self.Ht_chunk))
+            for q in range(self.world):
+                self.Ht[:, q * self.mc:(q + 1) * self.mc] = self.Ht_all[q]
+        else:
+            self.Ht[:, :self.mc] = self.Ht_chunk
+        ev[3].record()
+        # Q_inv = I - Ht^H Ht on the owned row blocks
+        Ht = self.Ht[:, :M]
+        self.gram_rows(Ht, self.Q, -1.0, 0.0)
+        for i in self.Q.owned:
+            blk = self.Q.block(i)[:, i * nb:]
+            _ffi.check(self.lib.mspde_add_diag(_ffi.current_stream(), _ffi.ptr(blk), blk.stride(0), blk.shape[0], c_double(1.0)),
+                       "add_diag")
+        ev[4].record()
+        acc = self.cholesky(self.Q, y=self.y)
+        if self.world > 1:
+            dist.all_reduce(acc)
+            dist.all_reduce(self.info, op=dist.ReduceOp.MAX)
+        ev[5].record()
+        torch.cuda.synchronize()
+        names = ["gram_N", "chol_N", "trsm", "gram_M", "chol_M"]
+        self.timings = {nm: ev[k].elapsed_time(ev[k + 1]) for k, nm in enumerate(names)}
+        info = int(self.info[0].item())
+        if info:
+            self.info.zero_()
+        _ffi.check(info, "distributed Phi (Cholesky)")
+        a = acc.cpu()
+        return 0.5 * float(a[0]) - float(a[1])
