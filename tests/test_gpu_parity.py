@@ -441,3 +441,41 @@ def test_full_size_steps_are_reproducible(full):
         res.append((out.cpu(), Layers[2]._u_new.clone().cpu(), Layers[1]._u_new.clone().cpu()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
     assert torch.isfinite(res[0][1].abs()).all()
+
+
+def test_block_distributed_phi_matches_single_gpu(toy):
+    """mspde.dist.DistPhi (block-cyclic row layout, panel broadcasts) in a 1-rank NCCL group, several panels (nb=64),
+    against the single-GPU Phi.  The multi-rank equality and the n=96 run are in profiles/r01_dist_phi_*.log."""
+    import torch.distributed as dist
+    from mspde.dist import BlockRows, DistPhi
+    hp, pb, pt, ns, st, ctx0 = toy
+    from mspde.core import MspdeContext
+    hp8 = o.Hyper(n_layers=3, n=8, n_ext=64, n_theta=8)
+    pb8 = o.synthetic_problem(hp8)
+    ft, H, HtH, y, delta = pb8["ft"], pb8["H"], pb8["HtH"], pb8["y"], pb8["delta"]
+    ctx = MspdeContext(8, 64, H.shape[0], 3)
+    ctx.set_inputs(H, HtH, y, ft.D_diag, o.prior_tables(hp8, ft)["stdev_sym"], delta)
+    rng = np.random.default_rng(2)
+    u = o.symmetrize(o.w_half_from_normals(rng.standard_normal(ft.n_ravel), rng.standard_normal(ft.n_ravel))) * 3.0
+    L = ctx.construct_L(ctx.to_dev(u), 1.0e3)
+    ref = ctx.phi(L)
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", str(29600 + os.getpid() % 300))
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        dp = DistPhi(ctx.N, ctx.M, nb=64, device=ctx.device)
+        hr = BlockRows(ctx.N, 64, 1, 0, ctx.device)
+        for i in hr.owned:
+            hr.block(i).copy_(ctx.HtH[i * 64:i * 64 + hr.rows(i), :])
+        dp.setup(ctx.H, ctx.y, ctx.delta, HtH_rows=hr)
+        val = dp.phi(L)
+        assert abs(val - ref) <= RTOL * abs(ref), (val, ref)
+        dp2 = DistPhi(ctx.N, ctx.M, nb=128, device=ctx.device)
+        dp2.setup(ctx.H, ctx.y, ctx.delta)                 # HtH formed by the distributed Gram kernel
+        assert abs(dp2.phi(L) - ref) <= 1e-9 * abs(ref)
+    finally:
+        if created:
+            dist.destroy_process_group()

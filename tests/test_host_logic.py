@@ -74,3 +74,23 @@ def test_gather_samples_two_ranks_gloo():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res)
     assert all(abs(acc - 3 / 20) < 1e-12 for _, _, acc in res)
+
+
+def test_block_rows_layout():
+    """Ownership / offsets of the 1-D block-cyclic row layout used by the distributed Phi (index logic only, CPU)."""
+    from mspde.dist import BlockRows
+    n, nb = 1000, 128
+    seen = []
+    for rank in range(3):
+        br = BlockRows(n, nb, 3, rank, torch.device("cpu"))
+        assert br.owned == [i for i in range(8) if i % 3 == rank]
+        rows = sum(br.rows(i) for i in br.owned)
+        assert br.data.shape == (rows, 1000) and br.ld % 8 == 0
+        for i in br.owned:
+            assert br.block(i).shape == (min(nb, n - i * nb), n)
+            br.block(i).fill_(i)
+            seen.append(i)
+        for i in br.owned:
+            assert bool((br.block(i) == i).all())
+    assert sorted(seen) == list(range(8))
+    assert BlockRows(1000, 128, 3, 0, torch.device("cpu")).rows(7) == 1000 - 7 * 128

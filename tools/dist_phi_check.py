@@ -51,7 +51,7 @@ else:
     u = torch.zeros(N, dtype=torch.complex128, device=dev)
     half = torch.complex(torch.randn(N // 2 + 1, dtype=torch.float64, device=dev, generator=g), torch.randn(N // 2 + 1, dtype=torch.float64, device=dev, generator=g))
     kx = torch.as_tensor(f.ix.ravel("F")[N // 2:]).to(dev); ky = torch.as_tensor(f.iy.ravel("F")[N // 2:]).to(dev)
-    half = half * 30.0 / (1.0 + (kx.double() ** 2 + ky.double() ** 2)) ; half[0] = half[0].real
+    half = half * 30.0 / (1.0 + (kx.double() ** 2 + ky.double() ** 2)) ; half[0] = half[0].real.clone()
     u[N // 2:] = half; u[:N // 2] = torch.flip(half[1:], dims=(0,)).conj()
     L = ctx.construct_L(u, 1.13e5)
     y = torch.randn(M, dtype=torch.float64, device=dev, generator=g) * 30
