@@ -114,6 +114,12 @@ int mspde_zgemm_tn(void* stream, int conjA, int m, int n, int k, double alpha, c
 int mspde_zpotrf_upper(void* stream, void* A, int lda, int n, void* winv, int* info_dev);
 int mspde_ztrsm_uh(void* stream, const void* U, int ldu, const void* winv, int n, void* B, int ldb, int ncols);
 
+/* f4: Welford running mean / M2 of u(x) = irfft2(sample) and of exp(u(x)) (m x m doubles each, device), one call per
+ * recorded sample; count = number of samples including this one (util.updateWelford, mcmc/util_cupy.py:168-177;
+ * post_analysis.py:57-105).  variance = M2/count, sample variance = M2/(count-1) (finalizeWelford, 181-187). */
+int mspde_posterior_stats_update(mspde_ctx* ctx, const void* u_sym, long long count, double* mean_u, double* m2_u,
+                                 double* mean_ell, double* m2_ell);
+
 /* Helpers of the block-distributed Phi (mspde/dist.py): A[i][i] += v; and, for an upper-trapezoidal row
  * panel V (nrows x ncols, diagonal at column 0): rowsq[j] = |sum_{i>=j} V[j][i] y[i]|^2, rowlog[j] = log Re V[j][j]
  * (the pieces of 0.5*||y@C||^2 - sum log diag C, image_cupy.py:643). */

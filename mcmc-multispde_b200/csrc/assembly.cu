@@ -40,7 +40,7 @@ __global__ void field_stage1(const cplx* __restrict__ u, const cplx* __restrict_
 
 // img[x][y] = (1/m) Re sum_c T1[x][c] W^{(c-(n-1)) y};  fp = exp(img), fm = exp(-img)
 __global__ void field_stage2(const cplx* __restrict__ T1, const cplx* __restrict__ W, double* __restrict__ fp,
-                             double* __restrict__ fm, int n, int il, int m) {
+                             double* __restrict__ fm, double* __restrict__ img_out, int n, int il, int m) {
     extern __shared__ cplx srow[];
     const int x = blockIdx.x;
     for (int c = threadIdx.x; c < il; c += blockDim.x) srow[c] = T1[x * il + c];
@@ -55,6 +55,7 @@ __global__ void field_stage2(const cplx* __restrict__ T1, const cplx* __restrict
         const double img = acc / double(m);
         fp[x * m + y] = exp(img);
         fm[x * m + y] = exp(-img);
+        if (img_out) img_out[x * m + y] = img;
     }
 }
 
@@ -151,11 +152,48 @@ int field_coeffs(Ctx* c, const cplx* u_sym, cplx* tp_out, cplx* tm_out) {
     const int n = c->n, il = c->il, m = c->m;
     field_stage1<<<m, 64, 0, st>>>(u_sym, c->W, c->T1, n, il, m);
     MSPDE_LAUNCH_CHECK();
-    field_stage2<<<m, 128, il * sizeof(cplx), st>>>(c->T1, c->W, c->fp, c->fm, n, il, m);
+    field_stage2<<<m, 128, il * sizeof(cplx), st>>>(c->T1, c->W, c->fp, c->fm, nullptr, n, il, m);
     MSPDE_LAUNCH_CHECK();
     field_stage3<<<m, 64, 2 * m * sizeof(double), st>>>(c->fp, c->fm, c->W, c->G, n, m);
     MSPDE_LAUNCH_CHECK();
     field_stage4<<<il, 64, 0, st>>>(c->G, c->W, tp_out, tm_out, n, il, m);
+    MSPDE_LAUNCH_CHECK();
+    return 0;
+}
+
+// running mean / M2 (Welford) of the field u(x) = irfft2(sample) and of exp(u(x)) on the device, so that
+// histories need not be stored for the posterior statistics of /root/reference/post_analysis.py:57-105
+// (util.updateWelford, /root/reference/mcmc/util_cupy.py:168-177).  count is the sample count AFTER this update.
+__global__ void welford_kernel(const double* __restrict__ img, const double* __restrict__ ell, double count,
+                               double* __restrict__ mean_u, double* __restrict__ m2_u, double* __restrict__ mean_ell,
+                               double* __restrict__ m2_ell, int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    {
+        const double x = img[i], mu = mean_u[i];
+        const double delta = x - mu;
+        const double mu2 = mu + delta / count;
+        mean_u[i] = mu2;
+        m2_u[i] += delta * (x - mu2);
+    }
+    {
+        const double x = ell[i], mu = mean_ell[i];
+        const double delta = x - mu;
+        const double mu2 = mu + delta / count;
+        mean_ell[i] = mu2;
+        m2_ell[i] += delta * (x - mu2);
+    }
+}
+
+int posterior_stats_update(Ctx* c, const cplx* u_sym, long long count, double* mean_u, double* m2_u, double* mean_ell,
+                           double* m2_ell) {
+    cudaStream_t st = c->stream;
+    const int n = c->n, il = c->il, m = c->m;
+    field_stage1<<<m, 64, 0, st>>>(u_sym, c->W, c->T1, n, il, m);
+    MSPDE_LAUNCH_CHECK();
+    field_stage2<<<m, 128, il * sizeof(cplx), st>>>(c->T1, c->W, c->fp, c->fm, c->img, n, il, m);
+    MSPDE_LAUNCH_CHECK();
+    welford_kernel<<<(m * m + 255) / 256, 256, 0, st>>>(c->img, c->fp, double(count), mean_u, m2_u, mean_ell, m2_ell, m * m);
     MSPDE_LAUNCH_CHECK();
     return 0;
 }

@@ -65,6 +65,7 @@ int mspde_ctx_create_ex(mspde_ctx** out, int device, int n, int n_ext, int M, in
     CTX_ALLOC(T1, size_t(m) * il);
     CTX_ALLOC(fp, size_t(m) * m);
     CTX_ALLOC(fm, size_t(m) * m);
+    CTX_ALLOC(img, size_t(m) * m);
     CTX_ALLOC(G, size_t(2) * m * n);
     CTX_ALLOC(tp, size_t(il) * il);
     CTX_ALLOC(tm, size_t(il) * il);
@@ -223,6 +224,15 @@ int mspde_construct_L(mspde_ctx* h, const void* u_sym, double sqrt_beta, void* L
     int rc = field_coeffs(&h->c, (const cplx*)u_sym, h->c.tp, h->c.tm);
     if (rc) return rc;
     return assemble_L(&h->c, h->c.tp, h->c.tm, sqrt_beta, (cplx*)L, ldl);
+}
+
+int mspde_posterior_stats_update(mspde_ctx* h, const void* u_sym, long long count, double* mean_u, double* m2_u,
+                                 double* mean_ell, double* m2_ell) {
+    if (count < 1) {
+        set_error("mspde_posterior_stats_update: count must be >= 1 (it is the sample count after this update)");
+        return -1;
+    }
+    return posterior_stats_update(&h->c, (const cplx*)u_sym, count, mean_u, m2_u, mean_ell, m2_ell);
 }
 
 int mspde_phi(mspde_ctx* h, const void* L, int ldl, double* out3_dev) {

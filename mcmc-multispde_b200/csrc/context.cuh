@@ -37,6 +37,7 @@ struct Ctx {
     cplx* T1 = nullptr;       // m x il
     double* fp = nullptr;     // m x m   exp(+u)
     double* fm = nullptr;     // m x m   exp(-u)
+    double* img = nullptr;    // m x m   u(x) (posterior statistics only)
     cplx* G = nullptr;        // 2 x m x n
     cplx* tp = nullptr;       // il x il  sym2D(rfft2(exp(+u)))
     cplx* tm = nullptr;       // il x il
@@ -72,6 +73,8 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
 // assembly.cu
 int field_coeffs(Ctx* c, const cplx* u_sym, cplx* tp_out, cplx* tm_out);
 int assemble_L(Ctx* c, const cplx* tp, const cplx* tm, double sqrt_beta, cplx* L, int ldl);
+int posterior_stats_update(Ctx* c, const cplx* u_sym, long long count, double* mean_u, double* m2_u, double* mean_ell,
+                           double* m2_ell);
 // phi.cu
 int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3, bool serial = false);
 int add_diag(cudaStream_t st, cplx* A, int lda, int n, double v);

@@ -196,6 +196,17 @@ class MspdeContext:
         chain.phi_cur_valid = 1
         return out
 
+    def posterior_stats_update(self, u_sym, count: int, stats: dict):
+        """Welford update of stats = dict(mean_u, m2_u, mean_ell, m2_ell) (m x m float64 device tensors)."""
+        self._sync_stream()
+        _ffi.check(self.lib.mspde_posterior_stats_update(self._h, _ffi.ptr(u_sym), ctypes.c_longlong(int(count)),
+                                                         _ffi.ptr(stats["mean_u"]), _ffi.ptr(stats["m2_u"]),
+                                                         _ffi.ptr(stats["mean_ell"]), _ffi.ptr(stats["m2_ell"])), "stats")
+
+    def new_stats(self):
+        z = lambda: torch.zeros((self.m, self.m), dtype=torch.float64, device=self.device)
+        return dict(mean_u=z(), m2_u=z(), mean_ell=z(), m2_ell=z(), count=0)
+
     def check_info(self, what: str):
         info = self.lib.mspde_read_info(self._h, 1)
         _ffi.check(info, what)

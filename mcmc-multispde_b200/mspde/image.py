@@ -309,6 +309,7 @@ class pCN:
         self.use_naive_logRatio_implementation = False
         self.cache_phi_current = False      # results-preserving shortcut (SURVEY 8d note i); off = reference-faithful
         self.skip_gibbs = False
+        self.accumulate_stats = False       # on-device Welford mean/variance of every layer's field
         self.fast_phi = False               # determinant-lemma Phi (SURVEY 8d note ii); off = reference-faithful Woodbury
         self.noise_source = None            # object with draw_iteration() -> dict (injected noise), else device RNG
         self._inputs_set = False
@@ -425,6 +426,11 @@ class pCN:
             for k, l in enumerate(Layers):
                 l.record_sample(self._rec_host[k].numpy())
                 l.record_sqrt_beta()
+                if self.accumulate_stats:
+                    if l.stats is None:
+                        l.stats = self.ctx.new_stats()
+                    l.stats["count"] += 1
+                    self.ctx.posterior_stats_update(l._u_cur, l.stats["count"], l.stats)
         self.record_count += 1
         accepted_SqrtBeta = self.one_step_for_sqrtBetas(Layers) if self.use_beta_adaptation else 0      # 604-607
         return accepted, accepted_SqrtBeta
@@ -526,6 +532,14 @@ class Layer:
             self.new_log_L_det = logdet
         self.current_log_L_det = self.new_log_L_det
         self.i_record = 0
+        self.stats = None
+
+    def field_statistics(self):
+        """finalizeWelford (mcmc/util_cupy.py:181-187): dict of mean / variance / sample variance of u(x) and exp(u(x))."""
+        s = self.stats
+        c = s["count"]
+        return dict(count=c, u_mean=s["mean_u"], u_var=s["m2_u"] / c, u_s_var=s["m2_u"] / max(c - 1, 1),
+                    ell_mean=s["mean_ell"], ell_var=s["m2_ell"] / c, ell_s_var=s["m2_ell"] / max(c - 1, 1))
 
     def _ensure_two_L_buffers(self):
         lm = self.LMat
@@ -704,15 +718,6 @@ class Simulation:
             self.total_time = time.time() - start_time
 
     def save(self, file_name, include_history=False):
-        """Simulation.save (1012-1014) -- h5py is not in this image, so the same keys go into an .npz."""
-        out = {k: v for k, v in self.__dict__.items() if isinstance(v, (int, float, str, bool))}
-        for k, lay in enumerate(self.Layers):
-            out['Layers {}/samples_history'.format(k)] = lay.samples_history
-            out['Layers {}/sqrt_beta_history'.format(k)] = lay.sqrt_beta_history
-        out['fourier/basis_number'] = self.fourier.basis_number
-        out['fourier/extended_basis_number'] = self.fourier.extended_basis_number
-        out['measurement/sinogram'] = self.measurement.sinogram
-        out['measurement/theta'] = self.measurement.theta
-        out['measurement/target_image'] = self.measurement.target_image
-        out['measurement/stdev'] = self.measurement.stdev
-        np.savez_compressed(file_name, **out)
+        """Simulation.save (1012-1014): same key layout; HDF5 when h5py is available, else .npz (mspde/io.py)."""
+        from . import io
+        return io.save_simulation(self, file_name)

@@ -318,6 +318,25 @@ def test_sqrt_beta_move_vs_oracle():
     assert a in (0, 1) and b in (0, 1)
 
 
+def test_on_device_posterior_statistics(toy):
+    """f4: Welford mean/variance of u(x) and exp(u(x)) accumulated on the device vs numpy on the oracle's fields."""
+    hp, pb, pt, ns, st, ctx = toy
+    ft = pb["ft"]
+    rng = np.random.default_rng(9)
+    stats = ctx.new_stats()
+    fields = []
+    for k in range(7):
+        u = o.symmetrize(o.w_half_from_normals(rng.standard_normal(ft.n_ravel), rng.standard_normal(ft.n_ravel))) * (1 + k)
+        fields.append(o.irfft2(o.from_u_2D_ravel_to_uHalf_2D(u, ft.n), ft))
+        stats["count"] += 1
+        ctx.posterior_stats_update(ctx.to_dev(u), stats["count"], stats)
+    F = np.stack(fields)
+    assert rel(stats["mean_u"].cpu(), F.mean(0)) < 1e-12
+    assert rel((stats["m2_u"] / 7).cpu(), F.var(0)) < 1e-11
+    assert rel(stats["mean_ell"].cpu(), np.exp(F).mean(0)) < 1e-12
+    assert rel((stats["m2_ell"] / 6).cpu(), np.exp(F).var(0, ddof=1)) < 1e-10
+
+
 def test_chain_against_committed_golden(golden_dir, toy):
     """Same toy chain as tests/golden/oracle_chain_n4.npz (generated by oracle/make_golden.py in the build container)."""
     hp, pb, pt, ns_unused, st_unused, ctx = toy
@@ -351,6 +370,27 @@ def test_simulation_surface_small():
     assert 0.0 <= sim.acceptancePercentage <= 1.0
     L = sim.Layers[2].LMat.current_L
     assert abs(sim.pcn._log_ratio(L) - sim.pcn.last_step["phi_cur"]) >= 0.0     # callable on its own
+    # f3/f4: statistics, result file, chain continuation, FBP initialisation
+    from mspde import io
+    sim.pcn.accumulate_stats = True
+    sim.pcn.one_step(sim.Layers)
+    fs = sim.Layers[1].field_statistics()
+    assert fs["count"] == 1 and torch.isfinite(fs["u_mean"]).all()
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        fn = sim.save(os.path.join(d, "result_0.hdf5"))
+        last = io.load_last_samples(fn)
+        assert len(last) == 3 and np.array_equal(last[2], sim.Layers[2].samples_history[sim.Layers[2].i_record - 1])
+        sim2 = im.Simulation(n_layers=3, n_samples=3, n=4, n_extended=64, beta=0.5, kappa=5e9, sigma_0=4e7, sigma_v=3.2e4,
+                             sigma_scaling=0.4, meas_std=0.2, evaluation_interval=2, printProgress=False, seed=4,
+                             burn_percentage=25.0, enable_step_adaptation=True, pcn_variant="dunlop", phantom_name="shepp.png",
+                             n_theta=8)
+        io.initialize_from_file(sim2, fn)
+        assert rel(sim2.Layers[2].current_sample.cpu(), last[2]) < 1e-15
+        img = io.initialize_using_FBP(sim2)
+        assert img.shape == (127, 127) and np.isfinite(img).all()
+        sim2.pcn.set_chol_epsilon(1e-6)
+        sim2.run()
     # a non-positive-definite system must surface as numpy.linalg.LinAlgError (Simulation.run's only except clause)
     sim.pcn.ctx.update_scalars(delta=-1e30)
     with pytest.raises(np.linalg.LinAlgError):
