@@ -323,7 +323,7 @@ def main():
         ach = fl / (ms_k * 1e-3) / 1e12
         roofline = {"kernel": "zgemm_tn_kernel (DMMA m8n8k4), launch Q_inv = I - Ht^H Ht, upper triangle, m=n=%d k=%d" % (M, N),
                     "bound": "tensor", "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
-                    "traffic": 56.2e9, "traffic_source": "dram__bytes_read+write of this launch, profiles/r01_zgemm_assembly_full.ncu-rep", "ms_per_launch": ms_k,
+                    "traffic": 13.1e9, "traffic_source": "dram__bytes_read+write of this launch, profiles/r01_zgemm_full_v2.ncu-rep (grouped tile rasterisation; 56.2e9 before it)", "ms_per_launch": ms_k,
                     "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_fp64_probe.log); "
                                    "MEASURED_PEAKS.json has no FP64 entry",
                     "step_fp64": {"flops_per_step": f_iter, "achieved": f_iter / (ms_dev * 1e-3 / args.steps) / 1e12,

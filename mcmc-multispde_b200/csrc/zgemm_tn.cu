@@ -24,6 +24,7 @@ constexpr int BM = 64;          // C tile rows (i)
 constexpr int BN = 64;          // C tile cols (j), complex
 constexpr int BK = 16;          // complex k per stage
 constexpr int STAGES = 3;
+constexpr int GROUP_I = 16;     // row tiles per rasterisation group
 constexpr int PA = BM + 4;      // smem row pitch (complex); == 4 mod 8 -> conflict-free fragment loads
 constexpr int PB = BN + 4;
 constexpr int CONSUMER_WARPS = 8;
@@ -84,8 +85,15 @@ struct GemmArgs {
 };
 
 __global__ void __launch_bounds__(THREADS, 2) zgemm_tn_kernel(GemmArgs p) {
-    const int i0 = blockIdx.x * BM;
-    const int j0 = blockIdx.y * BN;
+    // Grouped rasterisation: consecutive CTAs walk GROUP_I row tiles x all column tiles, so one resident wave touches
+    // ~16 A panels + ~18 B panels (fits the 126 MB L2) instead of every A panel of the matrix.
+    const int tiles_i = (p.m + BM - 1) / BM, tiles_j = (p.n + BN - 1) / BN;
+    const int pid = blockIdx.x;
+    const int per_group = GROUP_I * tiles_j;
+    const int first_i = (pid / per_group) * GROUP_I;
+    const int gsize = min(tiles_i - first_i, GROUP_I);
+    const int i0 = (first_i + (pid % per_group) % gsize) * BM;
+    const int j0 = ((pid % per_group) / gsize) * BN;
     if (p.uplo == GEMM_UPPER && j0 + BN - 1 < i0) return;   // tile entirely below the diagonal
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -260,7 +268,7 @@ int launch(cudaStream_t st, const GemmArgs& a, int nz) {
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         g_attr_set = true;
     }
-    dim3 grid((a.m + BM - 1) / BM, (a.n + BN - 1) / BN, nz);
+    dim3 grid(((a.m + BM - 1) / BM) * ((a.n + BN - 1) / BN), 1, nz);
     zgemm_tn_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(a);
     MSPDE_LAUNCH_CHECK();
     return 0;
