@@ -58,9 +58,12 @@ int mspde_phi(mspde_ctx* ctx, const void* L, int ldl, double* out3_dev);
 int mspde_phi_fast(mspde_ctx* ctx, const void* L, int ldl, double* out3_dev);
 
 /* a5 + a8: cp.linalg.solve(L, w) (561, 681, 755, 785) and Lmatrix_2D.logDet (268-276; patch/norms.py:236-293).
+ * Blocked LU with partial pivoting (LAPACK pivot rule), right-hand side carried as an extra column.
  * x (N) <- L^-1 rhs; logabsdet_dev (device double, may be NULL) <- log|det L| = sum log|diag| of the factor.
  * L is not modified (it is copied into the workspace). */
 int mspde_solve(mspde_ctx* ctx, const void* L, int ldl, const void* rhs, void* x, double* logabsdet_dev);
+/* Same solve through Householder QR instead of the pivoted LU (independent check; log|det| = sum log|r_jj|). */
+int mspde_solve_qr(mspde_ctx* ctx, const void* L, int ldl, const void* rhs, void* x, double* logabsdet_dev);
 /* a11: util.lstsq(a, b) = reduced QR -> q^H b -> solve_triangular (mcmc/util_cupy.py:590-609,
  * mcmc/extra_linalg.py:15-106); a is rows x cols (rows >= cols, within the context's (M+N) x N workspace). */
 int mspde_lstsq(mspde_ctx* ctx, const void* a, int lda, int rows, int cols, const void* b, void* x);

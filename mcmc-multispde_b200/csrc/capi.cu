@@ -123,6 +123,10 @@ int mspde_ctx_create_ex(mspde_ctx** out, int device, int n, int n_ext, int M, in
         if (dmalloc(&w, qr_work_bytes(M + N, N))) { mspde_ctx_destroy(h); return -1; }
         h->owned.push_back(w);
         c.qr_work = w;
+        unsigned char* w2 = nullptr;
+        if (dmalloc(&w2, lu_work_bytes(N, N + 2))) { mspde_ctx_destroy(h); return -1; }
+        h->owned.push_back(w2);
+        c.lu_work = w2;
     }
     *out = h;
     return 0;
@@ -241,6 +245,10 @@ int mspde_phi(mspde_ctx* h, const void* L, int ldl, double* out3_dev) {
 
 int mspde_solve(mspde_ctx* h, const void* L, int ldl, const void* rhs, void* x, double* logabsdet_dev) {
     return solve_L(&h->c, (const cplx*)L, ldl, (const cplx*)rhs, (cplx*)x, logabsdet_dev ? logabsdet_dev : h->c.scal + 20);
+}
+
+int mspde_solve_qr(mspde_ctx* h, const void* L, int ldl, const void* rhs, void* x, double* logabsdet_dev) {
+    return solve_L_qr(&h->c, (const cplx*)L, ldl, (const cplx*)rhs, (cplx*)x, logabsdet_dev ? logabsdet_dev : h->c.scal + 20);
 }
 
 int mspde_lstsq(mspde_ctx* h, const void* a, int lda, int rows, int cols, const void* b, void* x) {

@@ -55,6 +55,7 @@ struct Ctx {
     cplx* QRaug = nullptr;    // (M+N) x ldA,  ldA = round8(N+1)
     int ldA = 0;
     void* qr_work = nullptr;
+    void* lu_work = nullptr;
     cplx* vecN = nullptr;     // scratch vectors (4 x (N+M))
     cplx* gvec = nullptr;     // H^H y (fast Phi formulation)
     bool g_valid = false;
@@ -65,7 +66,8 @@ struct Ctx {
 };
 
 // pcn.cu
-int solve_L(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* x, double* logabsdet);
+int solve_L(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* x, double* logabsdet);      // pivoted LU
+int solve_L_qr(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* x, double* logabsdet);   // Householder QR
 int gibbs_lstsq(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* v);
 int lstsq_general(Ctx* c, const cplx* A, int lda, int rows, int cols, const cplx* b, cplx* x);
 int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flags, double* out_dev, cplx* record_dev);

@@ -17,6 +17,12 @@ struct LookAhead {          // auxiliary stream + events for the panel look-ahea
 int potrf_upper(cudaStream_t st, cplx* A, int lda, int n, cplx* winv, int* info, const LookAhead* la = nullptr);
 int trsm_uh(cudaStream_t st, const cplx* U, int ldu, const cplx* winv, int n, cplx* B, int ldb, int ncols);
 
+// getrf.cu
+size_t lu_work_bytes(int n, int ntot);
+// In-place P A = L U (partial pivoting, LAPACK pivot rule) of the leading n x n block of A (n x (n+naug), row-major); the
+// naug trailing columns receive L^-1 P b.  *info (device) <- first zero pivot (1-based); logabs (device) <- sum log|u_jj|.
+int getrf_aug(cudaStream_t st, cplx* A, int lda, int n, int naug, void* work, int* info, double* logabs);
+
 // geqrf.cu
 size_t qr_work_bytes(int rows, int cols);
 // Householder QR of the leading `cols` columns of A (rows x (cols+naug), rows >= cols); the naug trailing columns

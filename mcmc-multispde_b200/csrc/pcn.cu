@@ -80,8 +80,21 @@ int copy2d(cudaStream_t st, cplx* dst, int ldd, const cplx* src, int lds, int ro
 
 }  // namespace
 
-// x = L^-1 rhs through Householder QR of L (backward stable, no pivoting needed); logabsdet = sum log |r_jj|.
+// x = L^-1 rhs by LU with partial pivoting (zgetrf + zgetrs semantics of cp.linalg.solve); logabsdet = sum log |u_jj|
+// (patch/norms.py:276).  A singular pivot sets the context's info flag like LAPACK's info > 0.
 int solve_L(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* x, double* logabsdet) {
+    const int N = c->N;
+    int rc = copy2d(c->stream, c->QRaug, c->ldA, L, ldl, N, N);
+    if (rc) return rc;
+    set_col_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(c->QRaug, c->ldA, N, rhs, N);
+    MSPDE_LAUNCH_CHECK();
+    rc = getrf_aug(c->stream, c->QRaug, c->ldA, N, 1, c->lu_work, c->info, logabsdet);
+    if (rc) return rc;
+    return trsv_upper_aug(c->stream, c->QRaug, c->ldA, N, N, x);
+}
+
+// Same solve through Householder QR of L (kept as an independent, equally backward-stable path; logabsdet = sum log |r_jj|).
+int solve_L_qr(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* x, double* logabsdet) {
     const int N = c->N;
     int rc = copy2d(c->stream, c->QRaug, c->ldA, L, ldl, N, N);
     if (rc) return rc;

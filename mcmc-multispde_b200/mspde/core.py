@@ -159,12 +159,16 @@ class MspdeContext:
         v = self.scal[:3].cpu().numpy()
         return (float(v[0]), float(v[1]), float(v[2])) if parts else float(v[0])
 
-    def solve(self, L, rhs, want_logdet: bool = False):
-        """x = L^-1 rhs (cp.linalg.solve call sites); optionally also log|det L| (Lmatrix_2D.logDet)."""
+    def solve(self, L, rhs, want_logdet: bool = False, method: str = "lu"):
+        """x = L^-1 rhs (cp.linalg.solve call sites); optionally also log|det L| (Lmatrix_2D.logDet).
+        method: "lu" (partial pivoting, default) or "qr" (Householder)."""
         self._sync_stream()
         x = torch.empty(self.N, dtype=CDTYPE, device=self.device)
         ld = self.scal[8:9]
-        _ffi.check(self.lib.mspde_solve(self._h, _ffi.ptr(L), L.stride(0), _ffi.ptr(rhs), _ffi.ptr(x), _ffi.ptr(ld)), "solve")
+        fn = self.lib.mspde_solve if method == "lu" else self.lib.mspde_solve_qr
+        _ffi.check(fn(self._h, _ffi.ptr(L), L.stride(0), _ffi.ptr(rhs), _ffi.ptr(x), _ffi.ptr(ld)), "solve")
+        if method == "lu" and want_logdet:
+            self.check_info("solve (singular matrix)")
         return (x, float(ld.item())) if want_logdet else x
 
     def lstsq(self, a, b):

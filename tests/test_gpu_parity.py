@@ -97,6 +97,32 @@ def test_potrf_and_trsm(lib, n):
     assert rel(X.cpu(), ref.cpu()) < 1e-11
 
 
+@pytest.mark.parametrize("n", [2, 3, 5, 8, 12])
+def test_pivoted_lu_solve_and_logdet(n):
+    """mspde_solve (blocked LU, partial pivoting, LAPACK pivot rule) vs cuSOLVER getrf/getrs and vs the QR path; random
+    complex matrices force row interchanges in every column.  A singular matrix must surface as LinAlgError (info > 0)."""
+    from mspde.core import MspdeContext
+    ctx = MspdeContext(n, 64, 64, 3)
+    N = ctx.N
+    ctx.set_inputs(np.zeros((64, N), np.complex128), np.zeros((N, N), np.complex128), np.zeros(64), np.ones(N), np.ones(N), 0.0)
+    L = crandn(N, N, seed=n)
+    w = crandn(N, seed=n + 100)
+    Lp = ctx.new_matrix(N, N); Lp.copy_(L)
+    x, ld = ctx.solve(Lp, w, want_logdet=True)
+    xq, ldq = ctx.solve(Lp, w, want_logdet=True, method="qr")
+    ref = torch.linalg.solve(L, w)
+    cond = float(torch.linalg.cond(L))
+    assert rel(x.cpu(), ref.cpu()) < 1e-13 * cond and rel(xq.cpu(), ref.cpu()) < 1e-13 * cond
+    ldr = float(torch.linalg.slogdet(L)[1])
+    assert abs(ld - ldr) <= 1e-12 * abs(ldr) and abs(ldq - ldr) <= 1e-12 * abs(ldr)
+    assert torch.equal(Lp, L)                                     # inputs are not modified (cp.linalg.solve semantics)
+    Ls = Lp.clone()
+    Ls[:, N // 2] = 0
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.solve(Ls, w, want_logdet=True)
+    ctx.close()
+
+
 def test_potrf_reports_not_positive_definite(lib):
     from mspde import _ffi
     n = 130
