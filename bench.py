@@ -164,6 +164,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cache-phi", action="store_true", help="also report the results-preserving cached-Phi(current) rate")
     ap.add_argument("--no-extras", action="store_true", help="skip the separately-reported results-preserving formulations")
+    ap.add_argument("--chains-per-gpu", type=int, default=1,
+                    help="config 4 (many independent chains): also report the throughput with this many chains in flight per GPU")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -303,6 +305,43 @@ def main():
                                               "note": "opt-in pCN.fast_phi: same Phi to <=1e-10 (tests), 4N^3+8/3N^3 flops per Phi "
                                                       "instead of F_Phi; NOT the reference-faithful headline"}
         pcn.fast_phi = False
+
+    if args.chains_per_gpu > 1:
+        # BASELINE configs[3]: independent chains sharded over the GPUs.  Several chains per GPU are kept in flight on their
+        # own streams (each with its own context), which fills the latency-bound gaps of one chain with the GEMMs of another.
+        C = args.chains_per_gpu
+        sims = [sim] + [im.Simulation(n_layers=K, n_samples=8, n=cfg["n"], n_extended=cfg["n_ext"], beta=0.3, kappa=5e9, sigma_0=4e7,
+                                      sigma_v=3.2e4, sigma_scaling=0.4, meas_std=0.2, evaluation_interval=10, printProgress=False,
+                                      seed=100 + rank * C + c, burn_percentage=25.0, enable_step_adaptation=True,
+                                      pcn_variant="dunlop", phantom_name="shepp.png", meas_type="tomo", n_theta=cfg["n_theta"],
+                                      verbose=False, device=local_rank) for c in range(1, C)]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(C)]
+        binds = []
+        for sm_ in sims:
+            sm_.pcn.set_chol_epsilon(1e-6)
+            sm_.pcn._ensure_inputs(sm_.Layers[0].stdev_sym_host)
+            binds.append(sm_.pcn._bind(sm_.Layers))
+        torch.cuda.synchronize()
+
+        def sweep(i):
+            for c in range(C):
+                with torch.cuda.stream(streams[c]):
+                    w, lu, wl, e = dev_noise[i % len(dev_noise)]
+                    sims[c].pcn.ctx.pcn_step(binds[c], w, lu, wl, e)
+        for i in range(2):
+            sweep(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            sweep(i)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        for sm_ in sims:
+            sm_.pcn.ctx.check_info("multi-chain run")
+        extra["multi_chain"] = {"chains_per_gpu": C, "value": world * C * args.steps / float(tt.item()), "unit": "iters/s",
+                                "note": "aggregate over all chains; independent chains, reference-faithful formulation"}
 
     # ---- roofline of the dominant kernel: zgemm_tn_kernel on its largest launch, Q_inv = I - Ht^H Ht (upper) ----
     roofline = None

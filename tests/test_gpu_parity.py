@@ -363,6 +363,36 @@ def test_on_device_posterior_statistics(toy):
     assert rel((stats["m2_ell"] / 6).cpu(), np.exp(F).var(0, ddof=1)) < 1e-10
 
 
+def test_config1_two_layer_chain_vs_oracle():
+    """BASELINE configs[0] geometry (2 layers, n=16, 45 angles: N=961, M=5715) -- the reference's CPU-runnable case:
+    two whole iterations against the oracle with injected noise (accept decisions identical, 1e-10 on Phi and samples)."""
+    from mspde.core import MspdeContext
+    hp = o.Hyper(n_layers=2, n=16, n_ext=64, n_theta=45, beta=0.2)
+    pb = o.synthetic_problem(hp)
+    ft, H, HtH, y, delta = pb["ft"], pb["H"], pb["HtH"], pb["y"], pb["delta"]
+    pt = o.prior_tables(hp, ft)
+    K, M = 2, H.shape[0]
+    ns = o.NoiseStream(21, K, ft.n_ravel, M)
+    st = o.init_chain(hp, ft, [ns.half() for _ in range(K)], [ns.half() for _ in range(K)])
+    ctx = MspdeContext(16, 64, M, K)
+    ctx.set_inputs(H, HtH, y, ft.D_diag, pt["stdev_sym"], delta)
+    cb = _load_chain(ctx, st)
+    rec = torch.zeros((K, ft.n_ravel), dtype=torch.complex128, device=ctx.device)
+    for it in range(2):
+        nz = ns.draw_iteration()
+        d = o.one_step(st, ft, H, HtH, y, delta, nz)
+        out = ctx.pcn_step(cb, [ctx.to_dev(w) for w in nz["w_half"]], nz["log_u"], ctx.to_dev(nz["w_last"]), ctx.to_dev(nz["e"]),
+                           record=rec)
+        ctx.check_info("step")
+        g = out.cpu().numpy()
+        assert int(g[0]) == int(d["accepted"]) and abs(d["log_ratio"] - d["log_u"]) > 1e-6
+        assert abs(g[2] - d["phi_cur"]) <= RTOL * abs(d["phi_cur"]) and abs(g[3] - d["phi_new"]) <= RTOL * abs(d["phi_new"])
+        for k in range(K):
+            assert rel(cb.u_new[k].cpu(), st.u_new_sym[k]) < RTOL
+            assert rel(rec[k].cpu(), o.current_halves(st, ft)[k]) < RTOL
+    ctx.close()
+
+
 def test_chain_against_committed_golden(golden_dir, toy):
     """Same toy chain as tests/golden/oracle_chain_n4.npz (generated by oracle/make_golden.py in the build container)."""
     hp, pb, pt, ns_unused, st_unused, ctx = toy
