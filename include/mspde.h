@@ -123,6 +123,22 @@ int mspde_ztrsm_uh(void* stream, const void* U, int ldu, const void* winv, int n
 int mspde_posterior_stats_update(mspde_ctx* ctx, const void* u_sym, long long count, double* mean_u, double* m2_u,
                                  double* mean_ell, double* m2_ell);
 
+/* Panel-level pieces of the blocked LU / QR for the block-distributed driver (mspde/dist.py): the owner of a
+ * 64-column panel factors it (mspde_*_panel), broadcasts the pieces named by mspde_*_work_layout (byte offset, byte size
+ * pairs inside the caller-allocated workspace: QR -> V, V^T, T; LU -> L^T, (L11^-1)^T, row moves), and every rank applies
+ * them to its own columns right of the panel (mspde_*_apply).  Same kernels as mspde_solve / mspde_lstsq. */
+long long mspde_qr_work_bytes(int rows, int cols);
+long long mspde_lu_work_bytes(int n, int ntot);
+int mspde_qr_work_layout(int rows, int cols, void* work, long long* out6_host);
+int mspde_lu_work_layout(int n, int ntot, void* work, long long* out6_host);
+int mspde_qr_panel(void* stream, void* Ap, int lda, int mp, int pw, int rows, int cols, void* work, double* logabs_dev);
+int mspde_qr_apply(void* stream, int mp, int rows, int cols, void* work, void* A2, int lda, int n2);
+int mspde_lu_panel(void* stream, void* Ap, int lda, int mp, int pw, int goff, int n, int ntot, void* work, int* info_dev,
+                   double* logabs_dev);
+int mspde_lu_apply(void* stream, int mp, int pw, int n, int ntot, void* work, void* A12, int lda, int n2);
+/* x <- R^-1 d for the upper triangle R of A[0:n,0:n], d = column dcol of A (ztrsm call site, extra_linalg.py:102). */
+int mspde_trsv_upper(void* stream, void* A, int lda, int n, int dcol, void* x);
+
 /* Helpers of the block-distributed Phi (mspde/dist.py): A[i][i] += v; and, for an upper-trapezoidal row
  * panel V (nrows x ncols, diagonal at column 0): rowsq[j] = |sum_{i>=j} V[j][i] y[i]|^2, rowlog[j] = log Re V[j][j]
  * (the pieces of 0.5*||y@C||^2 - sum log diag C, image_cupy.py:643). */

@@ -299,6 +299,28 @@ int mspde_tomography_H(void* stream, int M, int N, const double* r_flat, const d
     return tomography_H((cudaStream_t)stream, M, N, r_flat, theta_flat, ix, iy, n_r, n_theta, apply_fixes, (cplx*)H, ldh);
 }
 
+/* ---- panel-level entry points for the block-distributed LU / QR (mspde/dist.py) ---- */
+long long mspde_qr_work_bytes(int rows, int cols) { return (long long)qr_work_bytes(rows, cols); }
+long long mspde_lu_work_bytes(int n, int ntot) { return (long long)lu_work_bytes(n, ntot); }
+int mspde_qr_work_layout(int rows, int cols, void* work, long long* out6) { qr_work_layout(rows, cols, work, out6); return 0; }
+int mspde_lu_work_layout(int n, int ntot, void* work, long long* out6) { lu_work_layout(n, ntot, work, out6); return 0; }
+int mspde_qr_panel(void* stream, void* Ap, int lda, int mp, int pw, int rows, int cols, void* work, double* logabs_dev) {
+    return qr_panel_factor((cudaStream_t)stream, (cplx*)Ap, lda, mp, pw, rows, cols, work, logabs_dev);
+}
+int mspde_qr_apply(void* stream, int mp, int rows, int cols, void* work, void* A2, int lda, int n2) {
+    return qr_panel_apply((cudaStream_t)stream, mp, rows, cols, work, (cplx*)A2, lda, n2);
+}
+int mspde_lu_panel(void* stream, void* Ap, int lda, int mp, int pw, int goff, int n, int ntot, void* work, int* info_dev,
+                   double* logabs_dev) {
+    return lu_panel_factor((cudaStream_t)stream, (cplx*)Ap, lda, mp, pw, goff, n, ntot, work, info_dev, logabs_dev);
+}
+int mspde_lu_apply(void* stream, int mp, int pw, int n, int ntot, void* work, void* A12, int lda, int n2) {
+    return lu_panel_apply((cudaStream_t)stream, mp, pw, n, ntot, work, (cplx*)A12, lda, n2);
+}
+int mspde_trsv_upper(void* stream, void* A, int lda, int n, int dcol, void* x) {
+    return trsv_upper_aug((cudaStream_t)stream, (cplx*)A, lda, n, dcol, (cplx*)x);
+}
+
 int mspde_add_diag(void* stream, void* A, int lda, int n, double v) {
     return add_diag((cudaStream_t)stream, (cplx*)A, lda, n, v);
 }

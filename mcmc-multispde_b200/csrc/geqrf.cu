@@ -12,6 +12,7 @@
 //   2. V^H V (split-K zgemm_tn) -> larft_kernel builds the compact-WY factor T
 //   3. W = V^H A2 (split-K zgemm_tn), W <- T^H W (in-place leaf zgemm_tn), A2 -= V W (zgemm_tn, K = 64)
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include "linalg.cuh"
 
 namespace cg = cooperative_groups;
@@ -36,11 +37,18 @@ struct QrWork {
     cplx* dots;   // 2 x MAXG x PW   per-CTA partial dot products (double buffered)
     cplx* currow; // 2 x PW          current diagonal row (double buffered)
     unsigned* bar; // grid barrier counter
+    cplx* gslab;  // rows x SPITCH   panel slabs when they do not fit in shared memory (tall panels, e.g. n = 96)
     int ldvt, ldw, nsplit;
 };
 
 size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
 // split-K partial products: up to 148 slices of the 64 x 64 Gram matrix, or ~10 slices of the 64 x (cols+1) W panel
+constexpr size_t SMEM_SLAB_LIMIT = 200 * 1024;
+size_t gslab_bytes(int rows) {   // only needed when ceil(rows/148) rows x 65 complex exceed the shared-memory budget
+    const size_t slab = (size_t(rows) + MAXG - 1) / MAXG;
+    const bool need = slab * SPITCH * sizeof(cplx) > SMEM_SLAB_LIMIT || getenv("MSPDE_FORCE_GSLAB") != nullptr;
+    return need ? (size_t(rows) + MAXG) * SPITCH * sizeof(cplx) : 256;
+}
 size_t part_elems(int cols) {
     const size_t ldw = (cols + 1 + 7) / 8 * 8;
     const size_t a = size_t(149) * PW * PW, b = size_t(12) * PW * ldw;
@@ -69,9 +77,11 @@ __device__ __forceinline__ cplx ldcg(const cplx* p) { return __ldcg(p); }
 __global__ void __launch_bounds__(256) qr_panel_kernel(cplx* __restrict__ A, int lda, int mp, int pw, int slab,
                                                        cplx* __restrict__ V, cplx* __restrict__ Vt, int ldvt,
                                                        cplx* __restrict__ tau_out, cplx* dots, cplx* currow,
-                                                       double* __restrict__ logabs, unsigned* barrier_counter) {
+                                                       double* __restrict__ logabs, unsigned* barrier_counter,
+                                                       cplx* gslab) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    cplx* S = reinterpret_cast<cplx*>(sm_raw);   // [slab][SPITCH]
+    // slab of panel rows: shared memory when it fits, otherwise a CTA-private region of an L2-resident scratch buffer
+    cplx* S = gslab ? gslab + size_t(blockIdx.x) * slab * SPITCH : reinterpret_cast<cplx*>(sm_raw);   // [slab][SPITCH]
     __shared__ cplx red[4][PW];
     __shared__ cplx sdot[PW];
     __shared__ cplx srow[PW];
@@ -311,6 +321,7 @@ QrWork carve(void* work, int rows, int cols) {
     w.dots = (cplx*)take(size_t(2) * MAXG * PW * sizeof(cplx));
     w.currow = (cplx*)take(size_t(2) * PW * sizeof(cplx));
     w.bar = (unsigned*)take(256);
+    w.gslab = (cplx*)take(gslab_bytes(rows));
     return w;
 }
 
@@ -328,6 +339,7 @@ size_t qr_work_bytes(int rows, int cols) {
     b += 3 * align_up(size_t(PW) * PW * sizeof(cplx));
     b += align_up(size_t(2) * MAXG * PW * sizeof(cplx));
     b += align_up(size_t(2) * PW * sizeof(cplx));
+    b += align_up(gslab_bytes(rows));
     return b + 4096;
 }
 
@@ -343,56 +355,78 @@ static int init_attrs() {
     return 0;
 }
 
-int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs) {
+// Factor one 64-column panel Ap (mp rows x pw pivot columns, leading dimension lda): R and the reflectors in place, and in
+// the workspace (laid out by carve(work, rows, cols)) the explicit V (mp x 64), V^T (64 x ldvt) and the compact-WY T.
+int qr_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int rows, int cols, void* work, double* logabs) {
     if (init_attrs()) return -1;
     QrWork w = carve(work, rows, cols);
+    int G = min(MAXG, (mp + 63) / 64);
+    int slab = (mp + G - 1) / G;
+    G = (mp + slab - 1) / slab;
+    size_t smem = size_t(slab) * SPITCH * sizeof(cplx);
+    cplx* gslab = nullptr;
+    static const bool force_global = getenv("MSPDE_FORCE_GSLAB") != nullptr;   // test hook for the tall-panel path
+    if (force_global || smem > SMEM_SLAB_LIMIT) {   // tall panel: slabs live in the L2-resident scratch instead
+        gslab = w.gslab;
+        smem = 0;
+    }
+    cplx* V = w.V; cplx* Vt = w.Vt; int ldvt = w.ldvt; cplx* tau = w.tau; cplx* dots = w.dots; cplx* currow = w.currow;
+    int mp_ = mp, pw_ = pw, slab_ = slab, lda_ = lda;
+    double* la = logabs;
+    unsigned* bar = w.bar;
+    MSPDE_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+    void* args[] = {&Ap, &lda_, &mp_, &pw_, &slab_, &V, &Vt, &ldvt, &tau, &dots, &currow, &la, &bar, &gslab};
+    MSPDE_CUDA(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(G), dim3(256), args, smem, st));
+    ++g_launches;
+    // T from V^H V
+    int ns_g = (mp + 127) / 128;
+    if (ns_g > w.nsplit) ns_g = w.nsplit;
+    int rc = zgemm_tn_splitk(st, true, PW, PW, mp, 1.0, w.V, PW, w.V, PW, 0.0, w.Gm, PW, w.part, ns_g);
+    if (rc) return rc;
+    larft_kernel<<<1, 256, 2 * sizeof(cplx) * PW * (PW + 1), st>>>(w.Gm, w.tau, pw, w.T);
+    MSPDE_LAUNCH_CHECK();
+    return 0;
+}
+
+// A2 (mp x n2) <- (I - V T^H V^H) A2 with the V, V^T, T held in the workspace.
+int qr_panel_apply(cudaStream_t st, int mp, int rows, int cols, void* work, cplx* A2, int lda, int n2) {
+    if (n2 <= 0) return 0;
+    QrWork w = carve(work, rows, cols);
+    const int tiles = (n2 + 63) / 64;
+    int ns_w = (592 + tiles - 1) / tiles;                 // ~2 waves of 296 resident CTAs
+    const int ns_cap = (mp + 255) / 256;                  // keep >= 256 k per slice
+    if (ns_w > ns_cap) ns_w = ns_cap;
+    const int ns_fit = int(part_elems(cols) / (size_t(PW) * size_t(n2)));
+    if (ns_w > ns_fit) ns_w = ns_fit;                     // partial-product workspace
+    if (ns_w < 1) ns_w = 1;
+    int rc = zgemm_tn_splitk(st, true, PW, n2, mp, 1.0, w.V, PW, A2, lda, 0.0, w.W, w.ldw, w.part, ns_w);   // W = V^H A2
+    if (rc) return rc;
+    rc = zgemm_tn(st, true, PW, n2, PW, 1.0, w.T, PW, w.W, w.ldw, 0.0, w.W, w.ldw, GEMM_FULL);   // W <- T^H W (in place)
+    if (rc) return rc;
+    return zgemm_tn(st, false, mp, n2, PW, -1.0, w.Vt, w.ldvt, w.W, w.ldw, 1.0, A2, lda, GEMM_FULL);   // A2 -= V W
+}
+
+// byte offsets / sizes of the pieces of the workspace a distributed driver has to broadcast
+void qr_work_layout(int rows, int cols, void* work, long long* out6) {
+    QrWork w = carve(work, rows, cols);
+    unsigned char* base = reinterpret_cast<unsigned char*>(work);
+    out6[0] = reinterpret_cast<unsigned char*>(w.V) - base;   out6[1] = (long long)rows * PW * sizeof(cplx);
+    out6[2] = reinterpret_cast<unsigned char*>(w.Vt) - base;  out6[3] = (long long)PW * w.ldvt * sizeof(cplx);
+    out6[4] = reinterpret_cast<unsigned char*>(w.T) - base;   out6[5] = (long long)PW * PW * sizeof(cplx);
+}
+
+// Householder QR of the leading `cols` columns of Aaug (rows x (cols + naug)), trailing columns get Q^H applied.
+// logabs (device, optional) accumulates sum log |r_jj|.
+int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs) {
     if (logabs) MSPDE_CUDA(cudaMemsetAsync(logabs, 0, sizeof(double), st));
     const int ntot = cols + naug;
     for (int c0 = 0; c0 < cols; c0 += PW) {
         const int pw = min(PW, cols - c0);
         const int mp = rows - c0;
-        int G = min(MAXG, (mp + 63) / 64);
-        int slab = (mp + G - 1) / G;
-        G = (mp + slab - 1) / slab;
-        const size_t smem = size_t(slab) * SPITCH * sizeof(cplx);
-        if (smem > 200 * 1024) {
-            set_error("geqrf_aug: panel slab of %d rows does not fit in shared memory", slab);
-            return -1;
-        }
         cplx* Ap = A + size_t(c0) * lda + c0;
-        cplx* V = w.V; cplx* Vt = w.Vt; int ldvt = w.ldvt; cplx* tau = w.tau; cplx* dots = w.dots; cplx* currow = w.currow;
-        int mp_ = mp, pw_ = pw, slab_ = slab, lda_ = lda;
-        double* la = logabs;
-        unsigned* bar = w.bar;
-        MSPDE_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
-        void* args[] = {&Ap, &lda_, &mp_, &pw_, &slab_, &V, &Vt, &ldvt, &tau, &dots, &currow, &la, &bar};
-        MSPDE_CUDA(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(G), dim3(256), args, smem, st));
-        ++g_launches;
-        const int n2 = ntot - (c0 + pw);
-        if (n2 <= 0) continue;
-        // T from V^H V
-        int ns_g = (mp + 127) / 128;
-        if (ns_g > w.nsplit) ns_g = w.nsplit;
-        int rc = zgemm_tn_splitk(st, true, PW, PW, mp, 1.0, w.V, PW, w.V, PW, 0.0, w.Gm, PW, w.part, ns_g);
+        int rc = qr_panel_factor(st, Ap, lda, mp, pw, rows, cols, work, logabs);
         if (rc) return rc;
-        larft_kernel<<<1, 256, 2 * sizeof(cplx) * PW * (PW + 1), st>>>(w.Gm, w.tau, pw, w.T);
-        MSPDE_LAUNCH_CHECK();
-        cplx* A2 = Ap + pw;
-        // W = V^H A2
-        const int tiles = (n2 + 63) / 64;
-        int ns_w = (592 + tiles - 1) / tiles;                 // ~2 waves of 296 resident CTAs
-        const int ns_cap = (mp + 255) / 256;                  // keep >= 256 k per slice
-        if (ns_w > ns_cap) ns_w = ns_cap;
-        const int ns_fit = int(part_elems(cols) / (size_t(PW) * size_t(n2)));
-        if (ns_w > ns_fit) ns_w = ns_fit;                     // partial-product workspace
-        if (ns_w < 1) ns_w = 1;
-        rc = zgemm_tn_splitk(st, true, PW, n2, mp, 1.0, w.V, PW, A2, lda, 0.0, w.W, w.ldw, w.part, ns_w);
-        if (rc) return rc;
-        // W <- T^H W (in place: single row tile)
-        rc = zgemm_tn(st, true, PW, n2, PW, 1.0, w.T, PW, w.W, w.ldw, 0.0, w.W, w.ldw, GEMM_FULL);
-        if (rc) return rc;
-        // A2 -= V W
-        rc = zgemm_tn(st, false, mp, n2, PW, -1.0, w.Vt, w.ldvt, w.W, w.ldw, 1.0, A2, lda, GEMM_FULL);
+        rc = qr_panel_apply(st, mp, rows, cols, work, Ap + pw, lda, ntot - (c0 + pw));
         if (rc) return rc;
     }
     return 0;

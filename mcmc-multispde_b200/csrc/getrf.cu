@@ -14,6 +14,7 @@
 //                        diagonal block, plus the net row permutation of the panel (<= 128 moved rows).
 //   2. gather/scatter    apply that permutation to the columns right of the panel (fully parallel, no serial swaps)
 //   3. U12 = L11^-1 A12  in-place leaf zgemm_tn with the transposed inverse;  A22 -= L21 U12  zgemm_tn (K = 64)
+#include <cstdlib>
 #include "linalg.cuh"
 
 namespace mspde {
@@ -35,8 +36,17 @@ struct LuWork {
     int* crow;       // 2 x MAXG
     int* moves;      // [0] = count, then MAXMOVE dst, MAXMOVE src (panel-local rows)
     unsigned* bar;
+    cplx* gslab;     // panel slabs when they do not fit in shared memory
     int ldlt, ldt;
 };
+
+constexpr size_t SMEM_SLAB_LIMIT = 150 * 1024;
+size_t gslab_bytes(int n) {
+    size_t slab = (size_t(n) + MAXG - 1) / MAXG;
+    if (slab < PW) slab = PW;
+    const bool need = slab * SPITCH * sizeof(cplx) > SMEM_SLAB_LIMIT || getenv("MSPDE_FORCE_GSLAB") != nullptr;
+    return need ? (size_t(n) + MAXG * PW) * SPITCH * sizeof(cplx) : 256;
+}
 
 size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -59,9 +69,11 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(cplx* __restrict__ A, int
                                                        cplx* __restrict__ Lt, int ldlt, cplx* __restrict__ linvT,
                                                        cplx* crowdata, cplx* currow, double* cval, int* crow,
                                                        int* __restrict__ moves, double* __restrict__ logabs,
-                                                       int* __restrict__ info, unsigned* barrier_counter) {
+                                                       int* __restrict__ info, unsigned* barrier_counter, cplx* gslab) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    cplx* S = reinterpret_cast<cplx*>(sm_raw);   // [slab][SPITCH]
+    // slab of panel rows: shared memory when it fits, otherwise a CTA-private region of an L2-resident scratch buffer
+    cplx* S = gslab ? gslab + size_t(blockIdx.x) * slab * SPITCH : reinterpret_cast<cplx*>(sm_raw) + PW * SPITCH;
+    cplx* X = reinterpret_cast<cplx*>(sm_raw);   // [PW][SPITCH] scratch of CTA 0 for the inverse of the diagonal block
     __shared__ double wval[8];
     __shared__ int wrow[8];
     __shared__ cplx prow[PW], cur[PW];
@@ -204,7 +216,6 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(cplx* __restrict__ A, int
     // X = L11^-1 computed row by row: X[i][:] = e_i - sum_{k<i} L[i][k] X[k][:]; thread t owns column t of X
     __syncthreads();
     {
-        cplx* X = S + size_t(slab) * SPITCH;     // second region of the dynamic shared memory: [PW][SPITCH]
         if (tid < PW) {
             const int c = tid;
             for (int i = 0; i < PW; ++i) {
@@ -256,6 +267,7 @@ LuWork carve(void* work, int n, int ntot) {
     w.crow = (int*)take(size_t(2) * MAXG * sizeof(int));
     w.moves = (int*)take(size_t(1 + 2 * MAXMOVE) * sizeof(int));
     w.bar = (unsigned*)take(256);
+    w.gslab = (cplx*)take(gslab_bytes(n));
     return w;
 }
 
@@ -268,58 +280,79 @@ size_t lu_work_bytes(int n, int ntot) {
     return align_up(size_t(PW) * ldlt * sizeof(cplx)) + align_up(size_t(PW) * PW * sizeof(cplx)) +
            align_up(size_t(MAXMOVE) * ldt * sizeof(cplx)) + align_up(size_t(2) * MAXG * PW * sizeof(cplx)) +
            align_up(size_t(2) * PW * sizeof(cplx)) + align_up(size_t(2) * MAXG * sizeof(double)) +
-           align_up(size_t(2) * MAXG * sizeof(int)) + align_up(size_t(1 + 2 * MAXMOVE) * sizeof(int)) + 256 + 4096;
+           align_up(size_t(2) * MAXG * sizeof(int)) + align_up(size_t(1 + 2 * MAXMOVE) * sizeof(int)) + 256 +
+           align_up(gslab_bytes(n)) + 4096;
+}
+
+// One 64-column panel of the pivoted LU: Ap (mp rows x pw pivot columns) factored in place; the workspace (laid out by
+// carve(work, n, ntot)) receives L^T, (L11^-1)^T and the net row permutation of the panel.
+int lu_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int goff, int n, int ntot, void* work, int* info,
+                    double* logabs) {
+    if (!g_attr) {
+        MSPDE_CUDA(cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        g_attr = true;
+    }
+    LuWork w = carve(work, n, ntot);
+    int G = min(MAXG, (mp + 63) / 64);
+    int slab = (mp + G - 1) / G;
+    if (slab < PW) slab = PW;               // CTA 0 must hold the whole diagonal block
+    G = (mp + slab - 1) / slab;
+    size_t smem = (size_t(slab) + PW) * SPITCH * sizeof(cplx);
+    cplx* gslab = nullptr;
+    static const bool force_global = getenv("MSPDE_FORCE_GSLAB") != nullptr;   // test hook for the tall-panel path
+    if (force_global || size_t(slab) * SPITCH * sizeof(cplx) > SMEM_SLAB_LIMIT) {   // tall panel: slabs live in the L2-resident scratch
+        gslab = w.gslab;
+        smem = size_t(PW) * SPITCH * sizeof(cplx);
+    }
+    MSPDE_CUDA(cudaMemsetAsync(w.bar, 0, sizeof(unsigned), st));
+    int lda_ = lda, mp_ = mp, pw_ = pw, slab_ = slab, goff_ = goff, ldlt = w.ldlt;
+    cplx* Lt = w.Lt; cplx* linvT = w.linvT; cplx* crowdata = w.crowdata; cplx* currow = w.currow;
+    double* cval = w.cval; int* crow = w.crow; int* moves = w.moves; double* la = logabs; int* inf = info;
+    unsigned* bar = w.bar;
+    void* args[] = {&Ap, &lda_, &mp_, &pw_, &slab_, &goff_, &Lt, &ldlt, &linvT, &crowdata, &currow, &cval, &crow,
+                    &moves, &la, &inf, &bar, &gslab};
+    MSPDE_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(G), dim3(256), args, smem, st));
+    ++g_launches;
+    return 0;
+}
+
+// Apply a factored panel to n2 columns right of it: A12 points at (panel row 0, first of those columns); rows are
+// permuted, U12 = L11^-1 A12 (first pw rows), then the mp - pw rows below get -= L21 U12.
+int lu_panel_apply(cudaStream_t st, int mp, int pw, int n, int ntot, void* work, cplx* A12, int lda, int n2) {
+    if (n2 <= 0) return 0;
+    LuWork w = carve(work, n, ntot);
+    gather_rows_kernel<<<dim3((n2 + 255) / 256, MAXMOVE), 256, 0, st>>>(A12, lda, w.moves, n2, w.tmp, w.ldt);
+    MSPDE_LAUNCH_CHECK();
+    scatter_rows_kernel<<<dim3((n2 + 255) / 256, MAXMOVE), 256, 0, st>>>(A12, lda, w.moves, n2, w.tmp, w.ldt);
+    MSPDE_LAUNCH_CHECK();
+    int rc = zgemm_tn(st, false, pw, n2, pw, 1.0, w.linvT, PW, A12, lda, 0.0, A12, lda, GEMM_FULL);   // in place, one row tile
+    if (rc) return rc;
+    if (mp > pw)
+        rc = zgemm_tn(st, false, mp - pw, n2, pw, -1.0, w.Lt + pw, w.ldlt, A12, lda, 1.0, A12 + size_t(pw) * lda, lda, GEMM_FULL);
+    return rc;
+}
+
+void lu_work_layout(int n, int ntot, void* work, long long* out6) {
+    LuWork w = carve(work, n, ntot);
+    unsigned char* base = reinterpret_cast<unsigned char*>(work);
+    out6[0] = reinterpret_cast<unsigned char*>(w.Lt) - base;     out6[1] = (long long)PW * w.ldlt * sizeof(cplx);
+    out6[2] = reinterpret_cast<unsigned char*>(w.linvT) - base;  out6[3] = (long long)PW * PW * sizeof(cplx);
+    out6[4] = reinterpret_cast<unsigned char*>(w.moves) - base;  out6[5] = (long long)(1 + 2 * MAXMOVE) * sizeof(int);
 }
 
 // In-place P A = L U of the leading n x n block of A (n x (n + naug)); the naug trailing columns receive L^-1 P b.
 // *info (device) <- first exactly-zero pivot (1-based) if any; logabs (device, optional) <- sum log |u_jj|.
 int getrf_aug(cudaStream_t st, cplx* A, int lda, int n, int naug, void* work, int* info, double* logabs) {
-    if (!g_attr) {
-        MSPDE_CUDA(cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        g_attr = true;
-    }
     const int ntot = n + naug;
-    LuWork w = carve(work, n, ntot);
     if (logabs) MSPDE_CUDA(cudaMemsetAsync(logabs, 0, sizeof(double), st));
     for (int c0 = 0; c0 < n; c0 += PW) {
         const int pw = min(PW, n - c0);
         const int mp = n - c0;
-        int G = min(MAXG, (mp + 63) / 64);
-        int slab = (mp + G - 1) / G;
-        if (slab < PW) slab = PW;               // CTA 0 must hold the whole diagonal block
-        G = (mp + slab - 1) / slab;
-        const size_t smem = (size_t(slab) + PW) * SPITCH * sizeof(cplx);
-        if (smem > 220 * 1024) {
-            set_error("getrf_aug: panel slab of %d rows does not fit in shared memory", slab);
-            return -1;
-        }
         cplx* Ap = A + size_t(c0) * lda + c0;
-        MSPDE_CUDA(cudaMemsetAsync(w.bar, 0, sizeof(unsigned), st));
-        int lda_ = lda, mp_ = mp, pw_ = pw, slab_ = slab, goff = c0, ldlt = w.ldlt;
-        cplx* Lt = w.Lt; cplx* linvT = w.linvT; cplx* crowdata = w.crowdata; cplx* currow = w.currow;
-        double* cval = w.cval; int* crow = w.crow; int* moves = w.moves; double* la = logabs; int* inf = info;
-        unsigned* bar = w.bar;
-        void* args[] = {&Ap, &lda_, &mp_, &pw_, &slab_, &goff, &Lt, &ldlt, &linvT, &crowdata, &currow, &cval, &crow,
-                        &moves, &la, &inf, &bar};
-        MSPDE_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(G), dim3(256), args, smem, st));
-        ++g_launches;
-        const int n2 = ntot - (c0 + pw);
-        if (n2 <= 0) continue;
-        cplx* A12 = Ap + pw;                     // rows of the panel's diagonal block, columns right of the panel
-        // row interchanges on the right part (rows are panel-local: offset by c0 through the base pointer)
-        gather_rows_kernel<<<dim3((n2 + 255) / 256, MAXMOVE), 256, 0, st>>>(A12, lda, w.moves, n2, w.tmp, w.ldt);
-        MSPDE_LAUNCH_CHECK();
-        scatter_rows_kernel<<<dim3((n2 + 255) / 256, MAXMOVE), 256, 0, st>>>(A12, lda, w.moves, n2, w.tmp, w.ldt);
-        MSPDE_LAUNCH_CHECK();
-        // U12 = L11^-1 A12 (in place, single row tile)
-        int rc = zgemm_tn(st, false, pw, n2, pw, 1.0, w.linvT, PW, A12, lda, 0.0, A12, lda, GEMM_FULL);
+        int rc = lu_panel_factor(st, Ap, lda, mp, pw, c0, n, ntot, work, info, logabs);
         if (rc) return rc;
-        // A22 -= L21 U12
-        if (mp > pw) {
-            rc = zgemm_tn(st, false, mp - pw, n2, pw, -1.0, w.Lt + pw, w.ldlt, A12, lda, 1.0, A12 + size_t(pw) * lda, lda,
-                          GEMM_FULL);
-            if (rc) return rc;
-        }
+        rc = lu_panel_apply(st, mp, pw, n, ntot, work, Ap + pw, lda, ntot - (c0 + pw));
+        if (rc) return rc;
     }
     return 0;
 }

@@ -22,12 +22,19 @@ size_t lu_work_bytes(int n, int ntot);
 // In-place P A = L U (partial pivoting, LAPACK pivot rule) of the leading n x n block of A (n x (n+naug), row-major); the
 // naug trailing columns receive L^-1 P b.  *info (device) <- first zero pivot (1-based); logabs (device) <- sum log|u_jj|.
 int getrf_aug(cudaStream_t st, cplx* A, int lda, int n, int naug, void* work, int* info, double* logabs);
+int lu_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int goff, int n, int ntot, void* work, int* info,
+                    double* logabs);
+int lu_panel_apply(cudaStream_t st, int mp, int pw, int n, int ntot, void* work, cplx* A12, int lda, int n2);
+void lu_work_layout(int n, int ntot, void* work, long long* out6);
 
 // geqrf.cu
 size_t qr_work_bytes(int rows, int cols);
 // Householder QR of the leading `cols` columns of A (rows x (cols+naug), rows >= cols); the naug trailing columns
 // receive Q^H applied.  logabs (device, optional) <- sum_j log|r_jj|.
 int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs);
+int qr_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int rows, int cols, void* work, double* logabs);
+int qr_panel_apply(cudaStream_t st, int mp, int rows, int cols, void* work, cplx* A2, int lda, int n2);
+void qr_work_layout(int rows, int cols, void* work, long long* out6);
 // x <- R^-1 d with R = upper triangle of A[0:n,0:n] and d = column dcol of A (d is overwritten).
 int trsv_upper_aug(cudaStream_t st, cplx* A, int lda, int n, int dcol, cplx* x);
 // Least squares min || A x - b ||: Aaug = [A | b] is rows x (cols+1) and is overwritten; x (cols) <- solution.

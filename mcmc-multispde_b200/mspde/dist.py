@@ -214,3 +214,163 @@ class DistPhi:
         _ffi.check(info, "distributed Phi (Cholesky)")
         a = acc.cpu()
         return 0.5 * float(a[0]) - float(a[1])
+
+
+# ======================================================================================================================
+# Block-distributed LU solve and QR least squares (the remaining dense pieces of one n=96 iteration)
+# ======================================================================================================================
+class BlockCols:
+    """Owned 64-column blocks of a rows x ntot matrix in a 1-D block-cyclic layout (block b on rank b mod P), stored as
+    one local row-major matrix whose columns are the owned blocks in ascending order."""
+
+    NB = 64
+
+    def __init__(self, rows, ntot, world, rank, device):
+        nb = self.NB
+        self.rows, self.ntot, self.world, self.rank = rows, ntot, world, rank
+        self.nblk = (ntot + nb - 1) // nb
+        self.owned = [b for b in range(self.nblk) if b % world == rank]
+        self.col0 = {}
+        c = 0
+        for b in self.owned:
+            self.col0[b] = c
+            c += self.width(b)
+        self.ncols = c
+        self.ld = _round_up(max(c, 1), 8)
+        self.data = torch.zeros((rows, self.ld), dtype=CDTYPE, device=device)
+
+    def width(self, b):
+        return min(self.NB, self.ntot - b * self.NB)
+
+    def right_of(self, p, pw):
+        """(local column offset, number of local columns) strictly right of panel p's pw pivot columns."""
+        if p in self.col0:
+            start = self.col0[p] + pw
+        else:
+            nxt = [b for b in self.owned if b > p]
+            start = self.col0[nxt[0]] if nxt else self.ncols
+        return start, self.ncols - start
+
+    def ptr(self, row, col):
+        return ctypes.c_void_p(self.data.data_ptr() + (row * self.ld + col) * 16)
+
+    def fill_from(self, full, aug=None):
+        """Columns < full.shape[1] come from the replicated matrix `full`; the remaining (augmented) columns from `aug`."""
+        nb, nreal = self.NB, full.shape[1]
+        for b in self.owned:
+            g0, w, l0 = b * nb, self.width(b), self.col0[b]
+            wr = max(0, min(w, nreal - g0))
+            if wr > 0:
+                self.data[:, l0:l0 + wr] = full[:, g0:g0 + wr]
+            if wr < w:
+                self.data[:, l0 + wr:l0 + w] = aug[:, g0 + wr - nreal:g0 + w - nreal]
+
+
+class _DistFactor:
+    def __init__(self, device=None):
+        self.lib = _ffi.lib()
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        for name in ("mspde_qr_work_bytes", "mspde_lu_work_bytes"):
+            getattr(self.lib, name).restype = ctypes.c_longlong
+
+    def _bcast_bytes(self, work, off, size, src):
+        if self.world > 1:
+            dist.broadcast(work[off:off + size], src=src)
+
+    def _gather_upper(self, mat: BlockCols, n, ntot):
+        """Every rank receives the upper-trapezoidal factor (rows < n) of the distributed matrix as one n x ntot matrix."""
+        nb = mat.NB
+        full = torch.zeros((n, _round_up(ntot, 8)), dtype=CDTYPE, device=self.device)[:, :ntot]
+        for b in range(mat.nblk):
+            w = mat.width(b)
+            nr = min(n, (b + 1) * nb)
+            buf = torch.empty((nr, w), dtype=CDTYPE, device=self.device)
+            if b % self.world == self.rank:
+                buf.copy_(mat.data[:nr, mat.col0[b]:mat.col0[b] + w])
+            if self.world > 1:
+                dist.broadcast(torch.view_as_real(buf), src=b % self.world)
+            full[:nr, b * nb:b * nb + w] = buf
+        return full
+
+    def _back_substitute(self, full, n, dcol):
+        x = torch.empty(n, dtype=CDTYPE, device=self.device)
+        _ffi.check(self.lib.mspde_trsv_upper(_ffi.current_stream(), _ffi.ptr(full), full.stride(0), n, dcol, _ffi.ptr(x)), "trsv")
+        return x
+
+
+class DistLU(_DistFactor):
+    """x = L^-1 rhs and log|det L| with the pivoted LU distributed over 64-column blocks (cp.linalg.solve, image_cupy.py:561)."""
+
+    def solve(self, L, rhs):
+        n = L.shape[0]
+        ntot = n + 1
+        mat = BlockCols(n, ntot, self.world, self.rank, self.device)
+        mat.fill_from(L, rhs.reshape(n, 1))
+        work = torch.empty(int(self.lib.mspde_lu_work_bytes(n, ntot)), dtype=torch.uint8, device=self.device)
+        lay = (ctypes.c_longlong * 6)()
+        self.lib.mspde_lu_work_layout(n, ntot, _ffi.ptr(work), lay)
+        logabs = torch.zeros(1, dtype=torch.float64, device=self.device)
+        info = torch.zeros(4, dtype=torch.int32, device=self.device)
+        st = _ffi.current_stream
+        nb = mat.NB
+        for p in range((n + nb - 1) // nb):
+            c0, owner = p * nb, p % self.world
+            pw, mp = min(nb, n - c0), n - c0
+            if self.rank == owner:
+                _ffi.check(self.lib.mspde_lu_panel(st(), mat.ptr(c0, mat.col0[p]), mat.ld, mp, pw, c0, n, ntot, _ffi.ptr(work),
+                                                   _ffi.ptr(info), _ffi.ptr(logabs)), "lu_panel")
+            for k in (0, 2, 4):
+                self._bcast_bytes(work, lay[k], lay[k + 1], owner)
+            start, n2 = mat.right_of(p, pw)
+            if n2 > 0:
+                _ffi.check(self.lib.mspde_lu_apply(st(), mp, pw, n, ntot, _ffi.ptr(work), mat.ptr(c0, start), mat.ld, n2), "lu_apply")
+        if self.world > 1:
+            dist.all_reduce(logabs)
+            dist.all_reduce(info, op=dist.ReduceOp.MAX)
+        full = self._gather_upper(mat, n, ntot)
+        x = self._back_substitute(full, n, n)
+        _ffi.check(int(info[0].item()), "distributed LU (singular matrix)")
+        return x, float(logabs.item())
+
+
+class DistQR(_DistFactor):
+    """v = argmin || [H; L] v - rhs || with the Householder QR distributed over 64-column blocks (util.lstsq, util_cupy.py:590-609)."""
+
+    def lstsq(self, blocks, rhs):
+        """blocks: list of replicated row blocks (e.g. [H, L]) stacked vertically; rhs: vector of the total row count."""
+        rows = sum(b.shape[0] for b in blocks)
+        n = blocks[0].shape[1]
+        ntot = n + 1
+        mat = BlockCols(rows, ntot, self.world, self.rank, self.device)
+        r0 = 0
+        nbk = mat.NB
+        for blk in blocks:                     # fill the owned columns block row by block row (no stacked copy is formed)
+            for b in mat.owned:
+                g0, w, l0 = b * nbk, mat.width(b), mat.col0[b]
+                wr = max(0, min(w, n - g0))
+                if wr > 0:
+                    mat.data[r0:r0 + blk.shape[0], l0:l0 + wr] = blk[:, g0:g0 + wr]
+            r0 += blk.shape[0]
+        last = mat.nblk - 1
+        if last in mat.col0:
+            mat.data[:, mat.col0[last] + (n - last * nbk)] = rhs
+        work = torch.empty(int(self.lib.mspde_qr_work_bytes(rows, n)), dtype=torch.uint8, device=self.device)
+        lay = (ctypes.c_longlong * 6)()
+        self.lib.mspde_qr_work_layout(rows, n, _ffi.ptr(work), lay)
+        st = _ffi.current_stream
+        for p in range((n + nbk - 1) // nbk):
+            c0, owner = p * nbk, p % self.world
+            pw, mp = min(nbk, n - c0), rows - c0
+            if self.rank == owner:
+                _ffi.check(self.lib.mspde_qr_panel(st(), mat.ptr(c0, mat.col0[p]), mat.ld, mp, pw, rows, n, _ffi.ptr(work), None),
+                           "qr_panel")
+            self._bcast_bytes(work, lay[0], mp * nbk * 16, owner)          # V: only the mp live rows
+            self._bcast_bytes(work, lay[2], lay[3], owner)                 # V^T
+            self._bcast_bytes(work, lay[4], lay[5], owner)                 # T
+            start, n2 = mat.right_of(p, pw)
+            if n2 > 0:
+                _ffi.check(self.lib.mspde_qr_apply(st(), mp, rows, n, _ffi.ptr(work), mat.ptr(c0, start), mat.ld, n2), "qr_apply")
+        full = self._gather_upper(mat, n, ntot)
+        return self._back_substitute(full, n, n)

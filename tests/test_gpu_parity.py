@@ -572,6 +572,16 @@ def test_block_distributed_phi_matches_single_gpu(toy):
         dp2 = DistPhi(ctx.N, ctx.M, nb=128, device=ctx.device)
         dp2.setup(ctx.H, ctx.y, ctx.delta)                 # HtH formed by the distributed Gram kernel
         assert abs(dp2.phi(L) - ref) <= 1e-9 * abs(ref)
+        # block-distributed pivoted LU and Householder QR drivers (panel factor on the owner, broadcast, local apply)
+        from mspde.dist import DistLU, DistQR
+        w = crandn(ctx.N, seed=11)
+        x1, ld1 = ctx.solve(L, w, want_logdet=True)
+        x2, ld2 = DistLU(ctx.device).solve(L, w)
+        assert torch.equal(x1, x2) and ld1 == ld2          # same kernels, same order: bit-identical
+        rhs = crandn(ctx.M + ctx.N, seed=12)
+        v1 = ctx.gibbs_lstsq(L, rhs)
+        v2 = DistQR(ctx.device).lstsq([ctx.H, L], rhs)
+        assert torch.equal(v1, v2)
     finally:
         if created:
             dist.destroy_process_group()

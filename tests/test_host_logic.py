@@ -94,3 +94,27 @@ def test_block_rows_layout():
             assert bool((br.block(i) == i).all())
     assert sorted(seen) == list(range(8))
     assert BlockRows(1000, 128, 3, 0, torch.device("cpu")).rows(7) == 1000 - 7 * 128
+
+
+def test_block_cols_layout():
+    """1-D block-cyclic column layout of the distributed LU / QR (index logic only, CPU)."""
+    from mspde.dist import BlockCols
+    rows, ntot = 10, 200            # 4 blocks: 64, 64, 64, 8
+    full = torch.arange(rows * 199, dtype=torch.float64).reshape(rows, 199).to(torch.complex128)
+    aug = torch.full((rows, 1), -1.0, dtype=torch.complex128)
+    cover = torch.zeros(ntot)
+    for rank in range(3):
+        bc = BlockCols(rows, ntot, 3, rank, torch.device("cpu"))
+        assert bc.owned == [b for b in range(4) if b % 3 == rank]
+        bc.fill_from(full, aug)
+        for b in bc.owned:
+            g0, w, l0 = b * 64, bc.width(b), bc.col0[b]
+            ref = torch.cat((full, aug), 1)[:, g0:g0 + w]
+            assert torch.equal(bc.data[:, l0:l0 + w], ref)
+            cover[g0:g0 + w] += 1
+        start, n2 = bc.right_of(0, 64)
+        assert n2 == sum(bc.width(b) for b in bc.owned if b > 0) and (n2 == 0 or start == bc.col0[[b for b in bc.owned if b > 0][0]])
+        if 3 in bc.col0:                                   # last block: 7 real columns + the augmented one
+            start, n2 = bc.right_of(3, 7)
+            assert n2 == 1 and bool((bc.data[:, start] == -1).all())
+    assert bool((cover == 1).all())
