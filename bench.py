@@ -34,6 +34,7 @@ CONFIGS = {
     1: dict(n=16, n_ext=64, n_theta=45, n_layers=2),
     2: dict(n=32, n_ext=64, n_theta=90, n_layers=3),
     3: dict(n=64, n_ext=64, n_theta=90, n_layers=3),
+    5: dict(n=96, n_ext=96, n_theta=90, n_layers=3),   # one chain, every dense piece block-distributed (needs >= 2 GPUs)
 }
 FP64_PEAK_TFLOPS = 37.15   # measured on this pool's B200: DMMA m8n8k4 microbenchmark, profiles/r01_fp64_probe.log
 
@@ -185,6 +186,32 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     f_iter, N, M = flops_iter(**cfg)
+    if args.config == 5:
+        # BASELINE configs[4]: a single n=96 chain whose dense work is block-distributed over the GPUs (strong scaling)
+        from mspde.dist import DistStep
+        if world < 2:
+            raise SystemExit("config 5 (n=96) needs at least 2 GPUs: python -m torch.distributed.run ... bench.py --config 5")
+        stp = DistStep(cfg["n"], cfg["n_ext"], cfg["n_theta"], dev)
+        for _ in range(min(args.warmup, 1)):
+            stp.run_once()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        runs = [stp.run_once() for _ in range(args.steps)]
+        clocks = sampler.stop()
+        sec = sum(r["seconds"] for r in runs) / len(runs)
+        if rank == 0:
+            print(json.dumps({"metric": "pCN iters/sec (n=96, 3 layers, one chain block-distributed)", "value": 1.0 / sec,
+                              "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1),
+                              "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                              "dtype": "f64", "data": "synthetic",
+                              "config": {"workload": "BASELINE configs[4]: 3 layers, n=96 (N=36481, M=17190), single chain, dense "
+                                                     "solves block-distributed over NCCL/NVLink", "pieces_s": runs[-1]["pieces_s"]},
+                              "roofline": {"bound": "tensor", "achieved": f_iter / sec / 1e12 / world, "peak": FP64_PEAK_TFLOPS,
+                                           "unit": "TFLOP/s per GPU", "frac": f_iter / sec / 1e12 / world / FP64_PEAK_TFLOPS,
+                                           "aggregate_tflops": f_iter / sec / 1e12, "traffic": None},
+                              "clocks": clocks, "finite": all(r["finite"] for r in runs)}))
+        dist.destroy_process_group()
+        return
     K = cfg["n_layers"]
     t_setup = time.perf_counter()
     sim = im.Simulation(n_layers=K, n_samples=args.steps * 2 + args.warmup * 2 + 8, n=cfg["n"], n_extended=cfg["n_ext"], beta=0.3,

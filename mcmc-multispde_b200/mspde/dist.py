@@ -374,3 +374,74 @@ class DistQR(_DistFactor):
                 _ffi.check(self.lib.mspde_qr_apply(st(), mp, rows, n, _ffi.ptr(work), mat.ptr(c0, start), mat.ld, n2), "qr_apply")
         full = self._gather_upper(mat, n, ntot)
         return self._back_substitute(full, n, n)
+
+
+class DistStep:
+    """All dense work of one pCN iteration (3 layers) with every piece block-distributed: replicated assembly, DistLU for the
+    middle-layer solve, DistPhi for Phi(current) and Phi(latest), DistQR for the Gibbs draw.  Used by bench.py --config 5 and
+    tools/dist_step_n96.py; hyper-parameters as in Simulation.__init__ (image_cupy.py:839-880)."""
+
+    def __init__(self, n, n_ext, n_theta, device, seed=7):
+        import numpy as np
+        from . import image as im, util
+        from .core import MspdeContext
+        self.device = device
+        il = 2 * n - 1
+        self.n, self.N, self.m = n, il * il, 2 * n_ext - 1
+        self.M, self.nr = self.m * n_theta, 2 * n * n - 2 * n + 1
+        N, M, nr = self.N, self.M, self.nr
+        f = im.FourierAnalysis_2D(n, n_ext)
+        sino = im.Sinogram("none.png", target_size=self.m, n_theta=n_theta, stdev=0.2)
+        self.H = sino.get_measurement_matrix_device(f.ix.ravel("F"), f.iy.ravel("F"), device) / 0.2
+        self.ctx = MspdeContext(n, n_ext, M, 3, device=device.index, assembly_only=True)
+        self._D = torch.as_tensor(f.D_diag).to(device)
+        _ffi.check(self.ctx.lib.mspde_ctx_set_inputs(self.ctx._h, None, 0, None, 0, None, 0, None, _ffi.ptr(self._D), None,
+                                                     c_double(0.0)))
+        pi = np.float64(util.PI)
+        beta_u = (4e7 ** 2) * 4 * pi
+        sb0 = np.float32(np.sqrt(beta_u))
+        self.sbv = float(np.float32(np.sqrt(beta_u * (3.2e4 / 4e7) ** 2)))
+        self.sb_mid = float(np.float64(np.float32(self.sbv)) * np.sqrt(0.4))
+        Lu = ((f.D_diag / 5e9 - 5e9) / np.float64(sb0)).astype(np.float32)
+        sd = -1.0 / Lu.astype(np.float64)
+        sd[nr - 1] /= 2
+        self.rng = np.random.Generator(np.random.PCG64(seed))
+        self._util = util
+        self.y = torch.as_tensor(self.rng.standard_normal(M) * 30).to(device)
+        self.rhs = torch.as_tensor(self.rng.standard_normal(M + N) + 0j).to(device)
+        self.u0 = torch.as_tensor(sd).to(device) * self._w_sym()
+        self.phi = DistPhi(N, M, nb=512, device=device)
+        self.phi.setup(self.H, self.y, 0.0)
+        nrm2 = torch.zeros(1, dtype=torch.float64, device=device)
+        for i in self.phi.HtH_rows.owned:      # delta = chol_epsilon * ||HtH||_F from the distributed row blocks (473-478)
+            blk = self.phi.HtH_rows.block(i)[:, i * 512:]
+            nrm2 += 2 * (torch.triu(blk, 1).abs() ** 2).sum() + (blk.diagonal().abs() ** 2).sum()
+        if dist.get_world_size() > 1:
+            dist.all_reduce(nrm2)
+        self.phi.delta = 1e-6 * float(nrm2.sqrt())
+        self.lu, self.qr = DistLU(device), DistQR(device)
+
+    def _w_sym(self):
+        u, r, nr = self._util, self.rng, self.nr
+        return torch.as_tensor(u.symmetrize(u.w_half_from_normals(r.standard_normal(nr), r.standard_normal(nr)))).to(self.device)
+
+    def run_once(self):
+        import time
+        T = {}
+
+        def tic():
+            torch.cuda.synchronize()
+            if dist.get_world_size() > 1:
+                dist.barrier()
+            return time.perf_counter()
+        t0 = tic()
+        L1 = self.ctx.construct_L(self.u0, self.sb_mid); T["assemble_mid"] = tic() - t0
+        t = tic(); u1, logdet = self.lu.solve(L1, self._w_sym()); T["lu_solve"] = tic() - t
+        del L1
+        t = tic(); L2 = self.ctx.construct_L(u1, self.sbv); T["assemble_last"] = tic() - t
+        t = tic(); phi_a = self.phi.phi(L2); T["phi_current"] = tic() - t
+        t = tic(); phi_b = self.phi.phi(L2); T["phi_latest"] = tic() - t
+        t = tic(); v = self.qr.lstsq([self.H, L2], self.rhs); T["gibbs_qr"] = tic() - t
+        total = tic() - t0
+        return dict(seconds=total, pieces_s={k: round(x, 4) for k, x in T.items()}, phi=phi_a, phi_repeat_equal=phi_a == phi_b,
+                    logdet_L1=logdet, finite=bool(torch.isfinite(v.abs()).all() and torch.isfinite(u1.abs()).all()))
