@@ -243,10 +243,10 @@ __global__ void splitk_reduce_kernel(const cplx* __restrict__ part, int nsplit, 
 #pragma unroll
         for (int u = 0; u < 8; ++u) { ax[u] += v[u].x; ay[u] += v[u].y; }
     }
-    for (; s < nsplit; ++s) {
+    for (; s < nsplit; ++s) {   // tail (fewer than 8 slices left), still a fixed order
         cplx v = part[s * slice + idx];
-        ax[s & 7] += v.x;
-        ay[s & 7] += v.y;
+        ax[0] += v.x;
+        ay[0] += v.y;
     }
     const double sx = ((ax[0] + ax[1]) + (ax[2] + ax[3])) + ((ax[4] + ax[5]) + (ax[6] + ax[7]));
     const double sy = ((ay[0] + ay[1]) + (ay[2] + ay[3])) + ((ay[4] + ay[5]) + (ay[6] + ay[7]));
