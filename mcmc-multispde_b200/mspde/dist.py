@@ -56,8 +56,35 @@ class BlockRows:
         return self.data[r:r + self.rows(i), :self.n]
 
 
+def drive(tasks):
+    """Round-robin over (generator, torch.cuda.Stream) pairs: each `next` enqueues one panel's worth of kernels and NCCL calls
+    on that task's stream, so independent block-distributed factorizations overlap on the GPUs (one fills the other's
+    panel-phase bubbles).  Returns the generators' return values."""
+    results = [None] * len(tasks)
+    live = list(range(len(tasks)))
+    while live:
+        for i in list(live):
+            gen, stream = tasks[i]
+            with torch.cuda.stream(stream):
+                try:
+                    next(gen)
+                except StopIteration as e:
+                    results[i] = e.value
+                    live.remove(i)
+    return results
+
+
+def run_to_completion(gen):
+    try:
+        while True:
+            next(gen)
+    except StopIteration as e:
+        return e.value
+
+
 class DistPhi:
-    def __init__(self, N, M, nb=512, device=None):
+    def __init__(self, N, M, nb=512, device=None, group=None):
+        self.group = group
         self.lib = _ffi.lib()
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
@@ -65,6 +92,7 @@ class DistPhi:
         self.N, self.M, self.nb = N, M, nb
         self.info = torch.zeros(4, dtype=torch.int32, device=self.device)
         self.timings = {}
+        self._events = None
 
     # ---- thin C-ABI wrappers on strided views ------------------------------------------------------------------
     def _gemm(self, A, B, C, alpha, beta, upper):
@@ -92,7 +120,10 @@ class DistPhi:
             self._gemm(A[:, c0:c0 + out.rows(i)], A[:, c0:], blk[:, c0:], alpha, beta, True)
 
     def cholesky(self, mat: BlockRows, keep_full=None, winv_all=None, y=None):
-        """In-place distributed upper Cholesky.  keep_full: optional n x n buffer receiving the complete factor (panels are
+        return run_to_completion(self.cholesky_gen(mat, keep_full, winv_all, y))
+
+    def cholesky_gen(self, mat: BlockRows, keep_full=None, winv_all=None, y=None):
+        """In-place distributed upper Cholesky (generator: yields after every panel).  keep_full: optional n x n buffer receiving the complete factor (panels are
         seen by every rank anyway).  winv_all: inverses of the 64-blocks (needed with keep_full for the later solve).
         y: if given, returns the local partial sums (sum |V y|^2 rows, sum log diag) of the owned panels."""
         n, nb, P = mat.n, mat.nb, self.world
@@ -121,9 +152,9 @@ class DistPhi:
                     acc[0] += rowsq[:bp].sum()
                     acc[1] += rowlog[:bp].sum()
             if P > 1:
-                dist.broadcast(torch.view_as_real(pv), src=owner)
+                dist.broadcast(torch.view_as_real(pv), src=owner, group=self.group)
                 if winv_all is not None:
-                    dist.broadcast(torch.view_as_real(wbuf), src=owner)
+                    dist.broadcast(torch.view_as_real(wbuf), src=owner, group=self.group)
             if keep_full is not None:
                 keep_full[c0:c0 + bp, c0:] = pv
             if winv_all is not None:
@@ -134,6 +165,7 @@ class DistPhi:
                 o = (i - p) * nb
                 bi = mat.rows(i)
                 self._gemm(pv[:, o:o + bi], pv[:, o:], mat.block(i)[:, i * nb:], -1.0, 1.0, True)
+            yield
         return acc
 
     # ---- Phi ---------------------------------------------------------------------------------------------------
@@ -167,9 +199,33 @@ class DistPhi:
 
     def phi(self, L):
         """Phi(L) for the replicated N x N matrix L; collective call, returns a Python float on every rank."""
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        acc = run_to_completion(self.phi_gen(L, timed=True))
+        ev1.record()
+        return self.finalize(acc)
+
+    def finalize(self, acc):
+        """Synchronise and turn the device-side sums of phi_gen into the Python float (raises LinAlgError on a failed Cholesky)."""
+        torch.cuda.synchronize()
+        if self._events:
+            names = ["gram_N", "chol_N", "trsm", "gram_M", "chol_M"]
+            self.timings = {nm: self._events[k].elapsed_time(self._events[k + 1]) for k, nm in enumerate(names)}
+        info = int(self.info[0].item())
+        if info:
+            self.info.zero_()
+        _ffi.check(info, "distributed Phi (Cholesky)")
+        a = acc.cpu()
+        return 0.5 * float(a[0]) - float(a[1])
+
+    def phi_gen(self, L, timed=False):
+        """Generator form of phi(): enqueues the work panel by panel on the current stream and returns the device tensor
+        {sum |V y|^2 rows, sum log diag V} (all-reduced); finalize() turns it into Phi."""
         N, M, nb = self.N, self.M, self.nb
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-        ev[0].record()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if timed else None
+        self._events = ev
+        mark = (lambda k: ev[k].record()) if timed else (lambda k: None)
+        mark(0)
         # r = HtH + delta I + L^H L on the owned row blocks
         self.r.data.copy_(self.HtH_rows.data)
         for i in self.r.owned:
@@ -177,21 +233,24 @@ class DistPhi:
             _ffi.check(self.lib.mspde_add_diag(_ffi.current_stream(), _ffi.ptr(blk), blk.stride(0), blk.shape[0],
                                                c_double(self.delta)), "add_diag")
         self.gram_rows(L, self.r, 1.0, 1.0)
-        ev[1].record()
-        self.cholesky(self.r, keep_full=self.U, winv_all=self.winv)
-        ev[2].record()
+        mark(1)
+        yield
+        yield from self.cholesky_gen(self.r, keep_full=self.U, winv_all=self.winv)
+        mark(2)
         # Ht = U^-H H^H for this rank's right-hand sides, then gather
         lo, hi = self._lohi
         if hi > lo:
             self.Ht_chunk[:, :hi - lo].copy_(self._Hct_chunk)
             self._trsm(self.U, self.winv, self.Ht_chunk)
+        yield
         if self.world > 1:
-            dist.all_gather_into_tensor(torch.view_as_real(self.Ht_all), torch.view_as_real(self.Ht_chunk))
+            dist.all_gather_into_tensor(torch.view_as_real(self.Ht_all), torch.view_as_real(self.Ht_chunk), group=self.group)
             for q in range(self.world):
                 self.Ht[:, q * self.mc:(q + 1) * self.mc] = self.Ht_all[q]
         else:
             self.Ht[:, :self.mc] = self.Ht_chunk
-        ev[3].record()
+        mark(3)
+        yield
         # Q_inv = I - Ht^H Ht on the owned row blocks
         Ht = self.Ht[:, :M]
         self.gram_rows(Ht, self.Q, -1.0, 0.0)
@@ -199,21 +258,14 @@ class DistPhi:
             blk = self.Q.block(i)[:, i * nb:]
             _ffi.check(self.lib.mspde_add_diag(_ffi.current_stream(), _ffi.ptr(blk), blk.stride(0), blk.shape[0], c_double(1.0)),
                        "add_diag")
-        ev[4].record()
-        acc = self.cholesky(self.Q, y=self.y)
+        mark(4)
+        yield
+        acc = yield from self.cholesky_gen(self.Q, y=self.y)
         if self.world > 1:
-            dist.all_reduce(acc)
-            dist.all_reduce(self.info, op=dist.ReduceOp.MAX)
-        ev[5].record()
-        torch.cuda.synchronize()
-        names = ["gram_N", "chol_N", "trsm", "gram_M", "chol_M"]
-        self.timings = {nm: ev[k].elapsed_time(ev[k + 1]) for k, nm in enumerate(names)}
-        info = int(self.info[0].item())
-        if info:
-            self.info.zero_()
-        _ffi.check(info, "distributed Phi (Cholesky)")
-        a = acc.cpu()
-        return 0.5 * float(a[0]) - float(a[1])
+            dist.all_reduce(acc, group=self.group)
+            dist.all_reduce(self.info, op=dist.ReduceOp.MAX, group=self.group)
+        mark(5)
+        return acc
 
 
 # ======================================================================================================================
@@ -267,7 +319,8 @@ class BlockCols:
 
 
 class _DistFactor:
-    def __init__(self, device=None):
+    def __init__(self, device=None, group=None):
+        self.group = group
         self.lib = _ffi.lib()
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
@@ -277,9 +330,12 @@ class _DistFactor:
 
     def _bcast_bytes(self, work, off, size, src):
         if self.world > 1:
-            dist.broadcast(work[off:off + size], src=src)
+            dist.broadcast(work[off:off + size], src=src, group=self.group)
 
     def _gather_upper(self, mat: BlockCols, n, ntot):
+        return run_to_completion(self._gather_upper_gen(mat, n, ntot))
+
+    def _gather_upper_gen(self, mat: BlockCols, n, ntot):
         """Every rank receives the upper-trapezoidal factor (rows < n) of the distributed matrix as one n x ntot matrix."""
         nb = mat.NB
         full = torch.zeros((n, _round_up(ntot, 8)), dtype=CDTYPE, device=self.device)[:, :ntot]
@@ -290,8 +346,10 @@ class _DistFactor:
             if b % self.world == self.rank:
                 buf.copy_(mat.data[:nr, mat.col0[b]:mat.col0[b] + w])
             if self.world > 1:
-                dist.broadcast(torch.view_as_real(buf), src=b % self.world)
+                dist.broadcast(torch.view_as_real(buf), src=b % self.world, group=self.group)
             full[:nr, b * nb:b * nb + w] = buf
+            if b % 8 == 7:
+                yield
         return full
 
     def _back_substitute(self, full, n, dcol):
@@ -304,6 +362,12 @@ class DistLU(_DistFactor):
     """x = L^-1 rhs and log|det L| with the pivoted LU distributed over 64-column blocks (cp.linalg.solve, image_cupy.py:561)."""
 
     def solve(self, L, rhs):
+        x, logabs, info = run_to_completion(self.solve_gen(L, rhs))
+        _ffi.check(int(info[0].item()), "distributed LU (singular matrix)")
+        return x, float(logabs.item())
+
+    def solve_gen(self, L, rhs):
+        """Generator: yields after every panel; returns (x, logabs tensor, info tensor) without synchronising."""
         n = L.shape[0]
         ntot = n + 1
         mat = BlockCols(n, ntot, self.world, self.rank, self.device)
@@ -326,13 +390,13 @@ class DistLU(_DistFactor):
             start, n2 = mat.right_of(p, pw)
             if n2 > 0:
                 _ffi.check(self.lib.mspde_lu_apply(st(), mp, pw, n, ntot, _ffi.ptr(work), mat.ptr(c0, start), mat.ld, n2), "lu_apply")
+            yield
         if self.world > 1:
-            dist.all_reduce(logabs)
-            dist.all_reduce(info, op=dist.ReduceOp.MAX)
-        full = self._gather_upper(mat, n, ntot)
+            dist.all_reduce(logabs, group=self.group)
+            dist.all_reduce(info, op=dist.ReduceOp.MAX, group=self.group)
+        full = yield from self._gather_upper_gen(mat, n, ntot)
         x = self._back_substitute(full, n, n)
-        _ffi.check(int(info[0].item()), "distributed LU (singular matrix)")
-        return x, float(logabs.item())
+        return x, logabs, info
 
 
 class DistQR(_DistFactor):
@@ -340,6 +404,9 @@ class DistQR(_DistFactor):
 
     def lstsq(self, blocks, rhs):
         """blocks: list of replicated row blocks (e.g. [H, L]) stacked vertically; rhs: vector of the total row count."""
+        return run_to_completion(self.lstsq_gen(blocks, rhs))
+
+    def lstsq_gen(self, blocks, rhs):
         rows = sum(b.shape[0] for b in blocks)
         n = blocks[0].shape[1]
         ntot = n + 1
@@ -372,7 +439,8 @@ class DistQR(_DistFactor):
             start, n2 = mat.right_of(p, pw)
             if n2 > 0:
                 _ffi.check(self.lib.mspde_qr_apply(st(), mp, rows, n, _ffi.ptr(work), mat.ptr(c0, start), mat.ld, n2), "qr_apply")
-        full = self._gather_upper(mat, n, ntot)
+            yield
+        full = yield from self._gather_upper_gen(mat, n, ntot)
         return self._back_substitute(full, n, n)
 
 
@@ -410,7 +478,11 @@ class DistStep:
         self.y = torch.as_tensor(self.rng.standard_normal(M) * 30).to(device)
         self.rhs = torch.as_tensor(self.rng.standard_normal(M + N) + 0j).to(device)
         self.u0 = torch.as_tensor(sd).to(device) * self._w_sym()
-        self.phi = DistPhi(N, M, nb=512, device=device)
+        world = dist.get_world_size()
+        self.gA = dist.new_group(list(range(world))) if world > 1 else None     # two communicators so that two
+        self.gB = dist.new_group(list(range(world))) if world > 1 else None     # factorizations can be in flight at once
+        self.sA, self.sB = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        self.phi = DistPhi(N, M, nb=512, device=device, group=self.gB)
         self.phi.setup(self.H, self.y, 0.0)
         nrm2 = torch.zeros(1, dtype=torch.float64, device=device)
         for i in self.phi.HtH_rows.owned:      # delta = chol_epsilon * ||HtH||_F from the distributed row blocks (473-478)
@@ -419,11 +491,45 @@ class DistStep:
         if dist.get_world_size() > 1:
             dist.all_reduce(nrm2)
         self.phi.delta = 1e-6 * float(nrm2.sqrt())
-        self.lu, self.qr = DistLU(device), DistQR(device)
+        self.lu, self.qr = DistLU(device, group=self.gA), DistQR(device, group=self.gA)
+        # a second Phi pipeline (own workspaces) so that Phi(current) can overlap the solve and Phi(latest) the Gibbs QR
+        self.L_cur = None
 
     def _w_sym(self):
         u, r, nr = self._util, self.rng, self.nr
         return torch.as_tensor(u.symmetrize(u.w_half_from_normals(r.standard_normal(nr), r.standard_normal(nr)))).to(self.device)
+
+    def run_overlapped(self):
+        """Same dense work as run_once, but the independent tasks are paired on two streams / two NCCL communicators:
+        (LU solve of the middle layer || Phi(L_current)) and then (Phi(L_latest) || Gibbs QR)."""
+        import time
+        main = torch.cuda.current_stream()
+        torch.cuda.synchronize()
+        if dist.get_world_size() > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        if self.L_cur is None:                       # the previous iteration's last-layer matrix
+            self.L_cur = self.ctx.construct_L(self.u0, self.sbv)
+        L1 = self.ctx.construct_L(self.u0, self.sb_mid)
+        w = self._w_sym()
+        self.sA.wait_stream(main); self.sB.wait_stream(main)
+        (x, logabs, info), acc_cur = drive([(self.lu.solve_gen(L1, w), self.sA), (self.phi.phi_gen(self.L_cur), self.sB)])
+        main.wait_stream(self.sA); main.wait_stream(self.sB)
+        phi_cur = self.phi.finalize(acc_cur)
+        t1 = time.perf_counter()
+        del L1
+        L2 = self.ctx.construct_L(x, self.sbv)
+        self.sA.wait_stream(main); self.sB.wait_stream(main)
+        v, acc_new = drive([(self.qr.lstsq_gen([self.H, L2], self.rhs), self.sA), (self.phi.phi_gen(L2), self.sB)])
+        main.wait_stream(self.sA); main.wait_stream(self.sB)
+        phi_new = self.phi.finalize(acc_new)
+        if dist.get_world_size() > 1:
+            dist.barrier()
+        total = time.perf_counter() - t0
+        self.L_cur = L2
+        return dict(seconds=total, pieces_s={"lu_solve||phi_current": round(t1 - t0, 4), "gibbs_qr||phi_latest": round(total - (t1 - t0), 4)},
+                    phi=phi_new, phi_current=phi_cur, logdet_L1=float(logabs.item()),
+                    finite=bool(torch.isfinite(v.abs()).all() and torch.isfinite(x.abs()).all()))
 
     def run_once(self):
         import time

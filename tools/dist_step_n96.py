@@ -10,7 +10,7 @@ dist.init_process_group("nccl", device_id=dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 stp = DistStep(n, max(n, 64), 90, dev)
 for rep in range(2):
-    r = stp.run_once()
+    r = stp.run_overlapped() if (len(sys.argv) > 2 and sys.argv[2] == "overlap") else stp.run_once()
     if dist.get_rank() == 0:
         print(json.dumps(dict(n=n, N=stp.N, M=stp.M, world=dist.get_world_size(), rep=rep, **r)), flush=True)
 dist.destroy_process_group()
