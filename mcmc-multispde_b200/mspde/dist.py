@@ -123,48 +123,75 @@ class DistPhi:
         return run_to_completion(self.cholesky_gen(mat, keep_full, winv_all, y))
 
     def cholesky_gen(self, mat: BlockRows, keep_full=None, winv_all=None, y=None):
-        """In-place distributed upper Cholesky (generator: yields after every panel).  keep_full: optional n x n buffer receiving the complete factor (panels are
-        seen by every rank anyway).  winv_all: inverses of the 64-blocks (needed with keep_full for the later solve).
-        y: if given, returns the local partial sums (sum |V y|^2 rows, sum log diag) of the owned panels."""
+        """In-place distributed upper Cholesky (generator: yields after every panel), look-ahead of one panel: the owner of
+        row block p+1 applies panel p to that block first, factorises it and starts its broadcast while every rank is still
+        busy with the rest of panel p's trailing update, so a panel factorisation stalls one rank instead of all of them.
+        keep_full: optional n x n buffer receiving the complete factor (panels are seen by every rank anyway).  winv_all:
+        inverses of the 64-blocks (needed with keep_full for the later solve).  y: if given, returns the local partial sums
+        (sum |V y|^2 rows, sum log diag) of the owned panels."""
         n, nb, P = mat.n, mat.nb, self.world
         nblk = mat.nblk
-        panel = torch.empty(nb * _round_up(n, 8), dtype=CDTYPE, device=self.device)
+        ldp = _round_up(n, 8)
+        panels = [torch.empty(nb * ldp, dtype=CDTYPE, device=self.device) for _ in range(2)]
         wblk = (nb // 64) * 64 * 64
-        wbuf = torch.empty(wblk, dtype=CDTYPE, device=self.device)
+        wbufs = [torch.empty(wblk, dtype=CDTYPE, device=self.device) for _ in range(2)]
         acc = torch.zeros(2, dtype=torch.float64, device=self.device)
         rowsq = torch.empty(nb, dtype=torch.float64, device=self.device)
         rowlog = torch.empty(nb, dtype=torch.float64, device=self.device)
-        for p in range(nblk):
-            owner = p % P
-            bp = mat.rows(p)
-            c0 = p * nb
+
+        def view(p):
+            bp, w = mat.rows(p), n - p * nb
+            return panels[p % 2][: bp * w].view(bp, w)
+
+        def factor(p):          # owner only: diagonal block + row panel, copy into the broadcast buffer
+            bp, c0 = mat.rows(p), p * nb
             w = n - c0
-            pv = panel[: bp * w].view(bp, w)
-            if self.rank == owner:
-                blk = mat.block(p)
-                self._potrf(blk[:, c0:c0 + bp], wbuf)
-                if w > bp:
-                    self._trsm(blk[:, c0:c0 + bp], wbuf, blk[:, c0 + bp:])
-                pv.copy_(blk[:, c0:])
-                if y is not None:
-                    _ffi.check(self.lib.mspde_upper_rows_times_y(_ffi.current_stream(), _ffi.ptr(pv), pv.stride(0), bp, w,
-                                                                 _ffi.ptr(y[c0:]), _ffi.ptr(rowsq), _ffi.ptr(rowlog)), "vy")
-                    acc[0] += rowsq[:bp].sum()
-                    acc[1] += rowlog[:bp].sum()
+            blk = mat.block(p)
+            self._potrf(blk[:, c0:c0 + bp], wbufs[p % 2])
+            if w > bp:
+                self._trsm(blk[:, c0:c0 + bp], wbufs[p % 2], blk[:, c0 + bp:])
+            pv = view(p)
+            pv.copy_(blk[:, c0:])
+            if y is not None:
+                _ffi.check(self.lib.mspde_upper_rows_times_y(_ffi.current_stream(), _ffi.ptr(pv), pv.stride(0), bp, w,
+                                                             _ffi.ptr(y[c0:]), _ffi.ptr(rowsq), _ffi.ptr(rowlog)), "vy")
+                acc[0] += rowsq[:bp].sum()
+                acc[1] += rowlog[:bp].sum()
+
+        def publish(p):         # everyone: receive panel p, keep the pieces of the factor that later steps need
+            owner = p % P
+            pv = view(p)
             if P > 1:
                 dist.broadcast(torch.view_as_real(pv), src=owner, group=self.group)
                 if winv_all is not None:
-                    dist.broadcast(torch.view_as_real(wbuf), src=owner, group=self.group)
+                    dist.broadcast(torch.view_as_real(wbufs[p % 2]), src=owner, group=self.group)
+            c0 = p * nb
             if keep_full is not None:
-                keep_full[c0:c0 + bp, c0:] = pv
+                keep_full[c0:c0 + mat.rows(p), c0:] = pv
             if winv_all is not None:
-                winv_all[p * wblk:(p + 1) * wblk] = wbuf
-            for i in mat.owned:                      # trailing update of the owned row blocks below the panel
-                if i <= p:
-                    continue
+                winv_all[p * wblk:(p + 1) * wblk] = wbufs[p % 2]
+
+        def update(p, blocks):  # trailing update of the given owned row blocks with panel p
+            pv = view(p)
+            for i in blocks:
                 o = (i - p) * nb
                 bi = mat.rows(i)
                 self._gemm(pv[:, o:o + bi], pv[:, o:], mat.block(i)[:, i * nb:], -1.0, 1.0, True)
+
+        if self.rank == 0:
+            factor(0)
+        publish(0)
+        for p in range(nblk):
+            mine = [i for i in mat.owned if i > p]
+            if p + 1 < nblk:
+                if self.rank == (p + 1) % P:
+                    update(p, [p + 1])
+                    factor(p + 1)
+                    publish(p + 1)
+                    update(p, [i for i in mine if i != p + 1])
+                else:
+                    update(p, mine)
+                    publish(p + 1)
             yield
         return acc
 
@@ -372,24 +399,55 @@ class DistLU(_DistFactor):
         ntot = n + 1
         mat = BlockCols(n, ntot, self.world, self.rank, self.device)
         mat.fill_from(L, rhs.reshape(n, 1))
-        work = torch.empty(int(self.lib.mspde_lu_work_bytes(n, ntot)), dtype=torch.uint8, device=self.device)
+        nbytes = int(self.lib.mspde_lu_work_bytes(n, ntot))
+        works = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
         lay = (ctypes.c_longlong * 6)()
-        self.lib.mspde_lu_work_layout(n, ntot, _ffi.ptr(work), lay)
+        self.lib.mspde_lu_work_layout(n, ntot, _ffi.ptr(works[0]), lay)
         logabs = torch.zeros(1, dtype=torch.float64, device=self.device)
         info = torch.zeros(4, dtype=torch.int32, device=self.device)
         st = _ffi.current_stream
         nb = mat.NB
-        for p in range((n + nb - 1) // nb):
-            c0, owner = p * nb, p % self.world
-            pw, mp = min(nb, n - c0), n - c0
-            if self.rank == owner:
-                _ffi.check(self.lib.mspde_lu_panel(st(), mat.ptr(c0, mat.col0[p]), mat.ld, mp, pw, c0, n, ntot, _ffi.ptr(work),
-                                                   _ffi.ptr(info), _ffi.ptr(logabs)), "lu_panel")
+        npan = (n + nb - 1) // nb
+        dims = lambda p: (p * nb, min(nb, n - p * nb), n - p * nb)       # c0, pw, mp
+
+        def factor(p):
+            c0, pw, mp = dims(p)
+            _ffi.check(self.lib.mspde_lu_panel(st(), mat.ptr(c0, mat.col0[p]), mat.ld, mp, pw, c0, n, ntot, _ffi.ptr(works[p % 2]),
+                                               _ffi.ptr(info), _ffi.ptr(logabs)), "lu_panel")
+
+        def publish(p):
             for k in (0, 2, 4):
-                self._bcast_bytes(work, lay[k], lay[k + 1], owner)
-            start, n2 = mat.right_of(p, pw)
+                self._bcast_bytes(works[p % 2], lay[k], lay[k + 1], p % self.world)
+
+        def apply(p, start, n2):
+            c0, pw, mp = dims(p)
             if n2 > 0:
-                _ffi.check(self.lib.mspde_lu_apply(st(), mp, pw, n, ntot, _ffi.ptr(work), mat.ptr(c0, start), mat.ld, n2), "lu_apply")
+                _ffi.check(self.lib.mspde_lu_apply(st(), mp, pw, n, ntot, _ffi.ptr(works[p % 2]), mat.ptr(c0, start), mat.ld, n2),
+                           "lu_apply")
+
+        # look-ahead of one panel: the owner of panel p+1 brings that block up to date and factors it before it joins the rest
+        # of panel p's trailing update; the other ranks update first and only then wait for the broadcast
+        if self.rank == 0:
+            factor(0)
+        publish(0)
+        for p in range(npan):
+            c0, pw, mp = dims(p)
+            start, n2 = mat.right_of(p, pw)
+            if p + 1 < npan:
+                if self.rank == (p + 1) % self.world:
+                    wn = mat.width(p + 1)
+                    s1 = mat.col0[p + 1]
+                    if p in mat.col0:          # single-rank group: panel p's own block may carry extra columns before block p+1
+                        apply(p, start, s1 - start)
+                    apply(p, s1, wn)
+                    factor(p + 1)
+                    publish(p + 1)
+                    apply(p, s1 + wn, mat.ncols - (s1 + wn))
+                else:
+                    apply(p, start, n2)
+                    publish(p + 1)
+            else:
+                apply(p, start, n2)
             yield
         if self.world > 1:
             dist.all_reduce(logabs, group=self.group)
@@ -423,22 +481,53 @@ class DistQR(_DistFactor):
         last = mat.nblk - 1
         if last in mat.col0:
             mat.data[:, mat.col0[last] + (n - last * nbk)] = rhs
-        work = torch.empty(int(self.lib.mspde_qr_work_bytes(rows, n)), dtype=torch.uint8, device=self.device)
+        nbytes = int(self.lib.mspde_qr_work_bytes(rows, n))
+        works = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
         lay = (ctypes.c_longlong * 6)()
-        self.lib.mspde_qr_work_layout(rows, n, _ffi.ptr(work), lay)
+        self.lib.mspde_qr_work_layout(rows, n, _ffi.ptr(works[0]), lay)
         st = _ffi.current_stream
-        for p in range((n + nbk - 1) // nbk):
-            c0, owner = p * nbk, p % self.world
-            pw, mp = min(nbk, n - c0), rows - c0
-            if self.rank == owner:
-                _ffi.check(self.lib.mspde_qr_panel(st(), mat.ptr(c0, mat.col0[p]), mat.ld, mp, pw, rows, n, _ffi.ptr(work), None),
-                           "qr_panel")
-            self._bcast_bytes(work, lay[0], mp * nbk * 16, owner)          # V: only the mp live rows
-            self._bcast_bytes(work, lay[2], lay[3], owner)                 # V^T
-            self._bcast_bytes(work, lay[4], lay[5], owner)                 # T
-            start, n2 = mat.right_of(p, pw)
+        npan = (n + nbk - 1) // nbk
+        dims = lambda p: (p * nbk, min(nbk, n - p * nbk), rows - p * nbk)     # c0, pw, mp
+
+        def factor(p):
+            c0, pw, mp = dims(p)
+            _ffi.check(self.lib.mspde_qr_panel(st(), mat.ptr(c0, mat.col0[p]), mat.ld, mp, pw, rows, n, _ffi.ptr(works[p % 2]), None),
+                       "qr_panel")
+
+        def publish(p):
+            c0, pw, mp = dims(p)
+            w, owner = works[p % 2], p % self.world
+            self._bcast_bytes(w, lay[0], mp * nbk * 16, owner)             # V: only the mp live rows
+            self._bcast_bytes(w, lay[2], lay[3], owner)                    # V^T
+            self._bcast_bytes(w, lay[4], lay[5], owner)                    # T
+
+        def apply(p, start, n2):
+            c0, pw, mp = dims(p)
             if n2 > 0:
-                _ffi.check(self.lib.mspde_qr_apply(st(), mp, rows, n, _ffi.ptr(work), mat.ptr(c0, start), mat.ld, n2), "qr_apply")
+                _ffi.check(self.lib.mspde_qr_apply(st(), mp, rows, n, _ffi.ptr(works[p % 2]), mat.ptr(c0, start), mat.ld, n2), "qr_apply")
+
+        # look-ahead of one panel (see DistLU.solve_gen)
+        if self.rank == 0:
+            factor(0)
+        publish(0)
+        for p in range(npan):
+            c0, pw, mp = dims(p)
+            start, n2 = mat.right_of(p, pw)
+            if p + 1 < npan:
+                if self.rank == (p + 1) % self.world:
+                    wn = mat.width(p + 1)
+                    s1 = mat.col0[p + 1]
+                    if p in mat.col0:
+                        apply(p, start, s1 - start)
+                    apply(p, s1, wn)
+                    factor(p + 1)
+                    publish(p + 1)
+                    apply(p, s1 + wn, mat.ncols - (s1 + wn))
+                else:
+                    apply(p, start, n2)
+                    publish(p + 1)
+            else:
+                apply(p, start, n2)
             yield
         full = yield from self._gather_upper_gen(mat, n, ntot)
         return self._back_substitute(full, n, n)
