@@ -193,10 +193,10 @@ def main():
             raise SystemExit("config 5 (n=96) needs at least 2 GPUs: python -m torch.distributed.run ... bench.py --config 5")
         stp = DistStep(cfg["n"], cfg["n_ext"], cfg["n_theta"], dev)
         for _ in range(min(args.warmup, 1)):
-            stp.run_once()
+            stp.run_overlapped()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        runs = [stp.run_once() for _ in range(args.steps)]
+        runs = [stp.run_overlapped() for _ in range(args.steps)]
         clocks = sampler.stop()
         sec = sum(r["seconds"] for r in runs) / len(runs)
         if rank == 0:
