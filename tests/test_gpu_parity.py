@@ -517,6 +517,82 @@ def test_full_size_solve_and_lstsq_properties(full):
     assert float((v - vref).abs().max()) <= 1e-9 * float(vref.abs().max())
 
 
+def _torch_assemble(fourier, u_sym, sqrt_beta, D):
+    """torch rendition (checker only) of Lmatrix_2D.construct_from: image_cupy.py:108-149, 171-179 + the BTTB gather."""
+    from mspde import util
+    n = fourier.basis_number
+    il = 2 * n - 1
+    uh = util.from_u_2D_ravel_to_uHalf_2D(u_sym, n)
+    img = fourier.irfft2(uh)
+    tp = util.symmetrize_2D(fourier.rfft2(torch.exp(img)))
+    tm = util.symmetrize_2D(fourier.rfft2(torch.exp(-img)))
+    idx = torch.arange(il * il, device=u_sym.device)
+    blk, inn = idx // il, idx % il
+    dij = blk[:, None] - blk[None, :]
+    dkl = inn[:, None] - inn[None, :]
+    mask = (dij.abs() <= n - 1) & (dkl.abs() <= n - 1)
+    r = (dkl + n - 1).clamp(0, il - 1)
+    c = (dij + n - 1).clamp(0, il - 1)
+    Up = torch.where(mask, tp[r, c], torch.zeros((), dtype=tp.dtype, device=tp.device))
+    Um = torch.where(mask, tm[r, c], torch.zeros((), dtype=tp.dtype, device=tp.device))
+    return (Up * D - Um) / sqrt_beta
+
+
+def test_full_size_step_vs_torch_rendition(full):
+    """One whole pCN iteration at BASELINE configs[1] size against a torch.linalg (cuFFT/cuBLAS/cuSOLVER) rendition of
+    pCN.one_step (image_cupy.py:553-617) fed the same injected noise: accept decision, both Phi values and every layer's new
+    sample.  torch is the checker here, never the product path."""
+    from mspde import util
+    pcn, ctx, Layers, f = full.pcn, full.pcn.ctx, full.Layers, full.fourier
+    K, N, M, nr = 3, ctx.N, ctx.M, ctx.n_ravel
+    rng = np.random.Generator(np.random.PCG64(17))
+    wh = [ctx.to_dev(util.w_half_from_normals(rng.standard_normal(nr), rng.standard_normal(nr))) for _ in range(K - 1)]
+    wl = ctx.to_dev(util.w_half_from_normals(rng.standard_normal(nr), rng.standard_normal(nr)))
+    e = ctx.to_dev(rng.standard_normal(M))
+    log_u = -0.7
+    beta, betaZ = pcn.beta, pcn.betaZ
+    # ---- rendition, from the state before the step
+    noise_cur = [l._noise_cur.clone() for l in Layers]
+    sd = ctx.stdev_sym
+    I_N = torch.eye(N, dtype=torch.complex128, device=ctx.device)
+
+    def phi_t(L):
+        r = L.conj().T @ L + ctx.HtH + ctx.delta * I_N
+        c = torch.linalg.cholesky(r)
+        Ht = torch.linalg.solve_triangular(c, ctx.Hct.contiguous(), upper=False)
+        Qi = torch.eye(M, dtype=torch.complex128, device=ctx.device) - Ht.conj().T @ Ht
+        C = torch.linalg.cholesky(Qi)
+        return 0.5 * float(torch.linalg.norm(ctx.y.to(torch.complex128) @ C) ** 2) - float(torch.log(torch.diagonal(C).real).sum())
+
+    n_new0 = betaZ * noise_cur[0] + beta * util.symmetrize(wh[0])
+    u0 = sd * n_new0
+    n_new1 = betaZ * noise_cur[1] + beta * util.symmetrize(wh[1])
+    L1 = _torch_assemble(f, u0, Layers[1].sqrt_beta, ctx.D_diag)
+    u1 = torch.linalg.solve(L1, n_new1)
+    del L1
+    phi_cur = phi_t(Layers[2].LMat.current_L.contiguous())
+    L2 = _torch_assemble(f, u1, Layers[2].sqrt_beta, ctx.D_diag)
+    phi_new = phi_t(L2)
+    accepted = (phi_cur - phi_new) > log_u
+    base = Layers[2]._noise_new.clone() if accepted else noise_cur[2]
+    n_new2 = betaZ * base + beta * util.symmetrize(wl)
+    rhs = torch.cat(((ctx.y - e).to(torch.complex128), -n_new2))
+    A = torch.cat((ctx.H.contiguous(), L2), 0)
+    v = torch.linalg.lstsq(A, rhs.unsqueeze(1)).solution.squeeze(1)
+    del A, L2
+    # ---- product path
+    cb = pcn._bind(Layers)
+    out = ctx.pcn_step(cb, wh, log_u, wl, e).cpu().numpy()
+    ctx.check_info("step")
+    assert int(out[0]) == int(accepted) and abs((phi_cur - phi_new) - log_u) > 1e-6
+    assert abs(out[2] - phi_cur) <= RTOL * abs(phi_cur) and abs(out[3] - phi_new) <= RTOL * abs(phi_new)
+    tol = 1e-9        # the dense solves amplify rounding by cond(L) ~ 1e4-1e5 on both sides
+    assert float((Layers[0]._u_new - u0).abs().max()) <= 1e-14 * float(u0.abs().max())
+    assert float((Layers[1]._u_new - u1).abs().max()) <= tol * float(u1.abs().max())
+    assert float((Layers[2]._noise_new - n_new2).abs().max()) <= 1e-14 * float(n_new2.abs().max())
+    assert float((Layers[2]._u_new - v).abs().max()) <= tol * float(v.abs().max())
+
+
 def test_full_size_steps_are_reproducible(full):
     """Two identical chains fed identical noise produce bit-identical results (deterministic reductions)."""
     from mspde import util
