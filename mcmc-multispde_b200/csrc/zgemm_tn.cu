@@ -14,6 +14,7 @@
 // lane of the k4 x n8 "col" fragment picks its component ((k'&1)^(n'&1)) and sign ((k'&1)&!(n'&1)) when
 // it loads from shared memory.  One DMMA.8x8x4 therefore performs a complex 8 x 4 x 2 product with no
 // wasted flops, and the accumulator fragment (row g, cols 2t,2t+1) is exactly one complex C element.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace mspde {
@@ -268,6 +269,8 @@ int launch(cudaStream_t st, const GemmArgs& a, int nz) {
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         g_attr_set = true;
     }
+    static FILE* logf = getenv("MSPDE_GEMM_LOG") ? fopen(getenv("MSPDE_GEMM_LOG"), "w") : nullptr;   // dev aid: shapes per launch
+    if (logf) { fprintf(logf, "%d %d %d %d %d\n", a.m, a.n, a.k, a.uplo, nz); fflush(logf); }
     dim3 grid(((a.m + BM - 1) / BM) * ((a.n + BN - 1) / BN), 1, nz);
     zgemm_tn_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(a);
     MSPDE_LAUNCH_CHECK();
