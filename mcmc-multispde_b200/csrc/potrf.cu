@@ -7,6 +7,7 @@
 // Leaves are 64 x 64 diagonal blocks handled by one CTA: the block is factorised with the trailing
 // matrix held in registers (one __syncthreads per column), then its triangular inverse is formed so
 // that the leaf solves become  X = inv(U11)^H B  -- again a zgemm_tn call (in place, one row tile).
+#include <cstdlib>
 #include "common.cuh"
 #include "linalg.cuh"
 
@@ -173,7 +174,7 @@ int potrf_upper(cudaStream_t st, cplx* A, int lda, int n, cplx* winv, int* info,
                                         (int)(NB * SP * sizeof(cplx))));
         g_attr = true;
     }
-    constexpr int NBO = 512;
+    static const int NBO = getenv("MSPDE_POTRF_NBO") ? atoi(getenv("MSPDE_POTRF_NBO")) : 512;   // outer panel width (multiple of 64)
     const bool ahead = la && la->aux && n > 2 * NBO;
     bool aux_pending = false;
     for (int j0 = 0; j0 < n; j0 += NBO) {

@@ -33,7 +33,7 @@ def main(argv=None):
     parser.add_argument('--seq-no', default=0, type=int)
     parser.add_argument('--n-layers', default=2, type=int)
     parser.add_argument('--n-theta', default=45, type=int)
-    parser.add_argument('--n', default=32, type=int)
+    parser.add_argument('--n', '--basis-n', dest='n', default=32, type=int)   # --basis-n: alias that survives torchrun's option parser
     parser.add_argument('--seed', default=1, type=int)
     parser.add_argument('--n-extended', default=64, type=int)
     parser.add_argument('--n-samples', default=100, type=int)
