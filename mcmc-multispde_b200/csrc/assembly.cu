@@ -8,6 +8,7 @@
 // divide).  Here L is written exactly once: each CTA stages the few table runs it needs (the "index map")
 // in shared memory and streams out 4 KB row segments with 16-byte stores.  m = 2 n_ext - 1 = 127 is
 // prime and the transforms are tiny, so the 2-D transforms are done as separable DFT sums in FP64.
+#include <cstdlib>
 #include "context.cuh"
 
 namespace mspde {
@@ -131,7 +132,10 @@ __global__ void __launch_bounds__(ACOLS) assemble_L_kernel(const cplx* __restric
     const int base = (j - jlo) * il;
     const double Dc = D[col];
     cplx* out = L + size_t(i) * il * ldl + col;
-    for (int k = 0; k < il; ++k) {
+    // the il rows of this block row are split over gridDim.z CTAs (more CTAs in flight, even tail)
+    const int kper = (il + gridDim.z - 1) / gridDim.z;
+    const int k0 = blockIdx.z * kper, k1 = min(il, k0 + kper);
+    for (int k = k0; k < k1; ++k) {
         const int d = k - l + (n - 1);
         cplx v = make_double2(0.0, 0.0);
         if (d >= 0 && d < il) {
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(ACOLS) assemble_L_kernel(const cplx* __restric
             v.x = __dmul_rn(__dsub_rn(__dmul_rn(a.x, Dc), b.x), inv_sb);
             v.y = __dmul_rn(__dsub_rn(__dmul_rn(a.y, Dc), b.y), inv_sb);
         }
-        out[size_t(k) * ldl] = v;
+        __stcs(reinterpret_cast<double2*>(out + size_t(k) * ldl), v);   // streaming store: L is consumed much later
     }
 }
 
@@ -200,7 +204,8 @@ int posterior_stats_update(Ctx* c, const cplx* u_sym, long long count, double* m
 
 int assemble_L(Ctx* c, const cplx* tp, const cplx* tm, double sqrt_beta, cplx* L, int ldl) {
     const int il = c->il, N = c->N;
-    dim3 grid((N + ACOLS - 1) / ACOLS, il);
+    static const int zsplit = getenv("MSPDE_ASM_Z") ? atoi(getenv("MSPDE_ASM_Z")) : 4;
+    dim3 grid((N + ACOLS - 1) / ACOLS, il, zsplit);
     const int njmax = ACOLS / il + 2;
     size_t smem = size_t(2) * njmax * il * sizeof(cplx);
     assemble_L_kernel<<<grid, ACOLS, smem, c->stream>>>(tp, tm, c->D_diag, 1.0 / sqrt_beta, L, ldl, c->n, il, N);
