@@ -395,6 +395,38 @@ def main():
                     "step_fp64": {"flops_per_step": f_iter, "achieved": f_iter / (ms_dev * 1e-3 / args.steps) / 1e12,
                                   "frac": f_iter / (ms_dev * 1e-3 / args.steps) / 1e12 / FP64_PEAK_TFLOPS}}
 
+    if rank == 0 and roofline is not None:
+        # HBM-bound kernels of the path (north_star: achieved HBM GB/s for assembly and misfit), timed live with CUDA events
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json (of measured)"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        import ctypes as _ct
+
+        def ev_ms(fn, reps=5):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        tp, tm = ctx.field_coeffs(Layers[1].current_sample_sym)
+        Lbuf = Layers[2].LMat.latest_computed_L
+        ms_a = ev_ms(lambda: ctx.assemble_L(tp, tm, 1.0e5, out=Lbuf))
+        Qv = ctx.buffer("Q", M, M)
+        rs, rl = torch.empty(M, dtype=torch.float64, device=dev), torch.empty(M, dtype=torch.float64, device=dev)
+        ms_v = ev_ms(lambda: lib.mspde_upper_rows_times_y(_ffi.current_stream(), _ffi.ptr(Qv), Qv.stride(0), M, M, _ffi.ptr(ctx.y),
+                                                          _ffi.ptr(rs), _ffi.ptr(rl)))
+        roofline["hbm_kernels"] = [
+            {"kernel": "assemble_L_kernel (a3+a4, one write pass of L)", "bound": "hbm", "bytes": 16.0 * N * N,
+             "achieved": 16.0 * N * N / ms_a * 1e-6, "peak": hbm_peak, "unit": "GB/s", "frac": 16.0 * N * N / ms_a * 1e-6 / hbm_peak,
+             "peak_source": hbm_src},
+            {"kernel": "vy_rows_kernel (misfit 0.5*||y@C||^2 - sum log diag C over the upper M x M factor)", "bound": "hbm",
+             "bytes": 8.0 * M * M, "achieved": 8.0 * M * M / ms_v * 1e-6, "peak": hbm_peak, "unit": "GB/s",
+             "frac": 8.0 * M * M / ms_v * 1e-6 / hbm_peak, "peak_source": hbm_src}]
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, desc, cores, dt = cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=30.0)
