@@ -682,3 +682,58 @@ def test_drivers_run_end_to_end(tmp_path):
     d = np.load(out)
     assert d["samples"].shape == (3, 3, 5, 25) and np.isfinite(d["samples"]).all()
     assert not np.array_equal(d["samples"][0], d["samples"][1])          # different seeds -> different chains
+
+
+def test_config3_size_phi_solve_and_lstsq():
+    """BASELINE configs[2] geometry (n=64: N=16129, M=11430): Phi against the torch.linalg rendition, the pivoted-LU solve
+    against cuSOLVER, and the optimality of the Gibbs least-squares solution (the oracle is out of reach at this size:
+    ~12 min per Phi on 8 host cores)."""
+    from mspde import image as im
+    sim = im.Simulation(n_layers=3, n_samples=2, n=64, n_extended=64, beta=0.3, kappa=5e9, sigma_0=4e7, sigma_v=3.2e4,
+                        sigma_scaling=0.4, meas_std=0.2, evaluation_interval=10, printProgress=False, seed=2, burn_percentage=25.0,
+                        enable_step_adaptation=True, pcn_variant="dunlop", phantom_name="shepp.png", n_theta=90)
+    sim.pcn.set_chol_epsilon(1e-6)
+    pcn, ctx = sim.pcn, sim.pcn.ctx
+    pcn._ensure_inputs(sim.Layers[0].stdev_sym_host)
+    N, M = ctx.N, ctx.M
+    assert (N, M) == (16129, 11430)
+    L = sim.Layers[2].LMat.current_L
+    phi = ctx.phi(L, parts=True)
+    Lc = L.contiguous()
+    r = Lc.conj().T @ Lc
+    r += ctx.HtH
+    r.diagonal().add_(ctx.delta)
+    c = torch.linalg.cholesky(r)
+    del r
+    Ht = torch.linalg.solve_triangular(c, ctx.Hct.contiguous(), upper=False)
+    del c
+    Qi = -(Ht.conj().T @ Ht)
+    Qi.diagonal().add_(1.0)
+    del Ht
+    C = torch.linalg.cholesky(Qi)
+    del Qi
+    quad = 0.5 * float(torch.linalg.norm(ctx.y.to(torch.complex128) @ C) ** 2)
+    logdet = float(torch.log(torch.diagonal(C).real).sum())
+    del C
+    ref = quad - logdet
+    assert abs(phi[0] - ref) <= RTOL * abs(ref), (phi, ref)
+    # dense solve of the middle layer
+    L1 = sim.Layers[1].LMat.current_L
+    w = sim.Layers[1].current_noise_sample
+    x, ld = ctx.solve(L1, w, want_logdet=True)
+    L1c = L1.contiguous()
+    xr = torch.linalg.solve(L1c, w)
+    assert float((x - xr).abs().max()) <= 1e-9 * float(xr.abs().max())
+    assert abs(ld - float(torch.linalg.slogdet(L1c)[1])) <= RTOL * abs(ld)
+    del L1c, xr
+    # Gibbs least squares: normal-equation residual
+    g = torch.Generator(device="cuda").manual_seed(9)
+    rhs = torch.complex(torch.randn(M + N, dtype=torch.float64, device="cuda", generator=g),
+                        torch.randn(M + N, dtype=torch.float64, device="cuda", generator=g))
+    v = ctx.gibbs_lstsq(L, rhs)
+    res_top = ctx.H @ v - rhs[:M]
+    res_bot = Lc @ v - rhs[M:]
+    grad = ctx.H.conj().T @ res_top + Lc.conj().T @ res_bot
+    scale = (float(torch.linalg.norm(ctx.H)) ** 2 + float(torch.linalg.norm(Lc)) ** 2) * float(torch.linalg.norm(v))
+    assert float(torch.linalg.norm(grad)) <= 1e-11 * scale
+    ctx.close()
