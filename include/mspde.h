@@ -53,6 +53,11 @@ int mspde_construct_L(mspde_ctx* ctx, const void* u_sym, double sqrt_beta, void*
 /* a9: pCN._log_ratio (619-662, default branch); out3 (device) = {Phi, 0.5*||y@C||^2, sum log diag C}. */
 int mspde_phi(mspde_ctx* ctx, const void* L, int ldl, double* out3_dev);
 
+/* f2: the reference's "naive" Phi (use_naive_logRatio_implementation, 644-657; no stabiliser): Z = solve(L^H, H^H) by a
+ * pivoted LU with M right-hand sides, C = chol(Z^H Z + I), Phi = 0.5*||C^-1 y||^2 + sum log diag C.
+ * out3 = {Phi, 0.5*||C^-1 y||^2, sum log diag C}. */
+int mspde_phi_naive(mspde_ctx* ctx, const void* L, int ldl, double* out3_dev);
+
 /* Same Phi through the determinant lemma (algorithm note ii): no M-sized work.  Opt-in; results agree with
  * mspde_phi to rounding (validated at 1e-10 in tests); reported separately from the reference-faithful path. */
 int mspde_phi_fast(mspde_ctx* ctx, const void* L, int ldl, double* out3_dev);
@@ -94,7 +99,8 @@ typedef struct {
 } mspde_step_noise;
 
 enum { MSPDE_STEP_CACHE_PHI_CUR = 1, MSPDE_STEP_SKIP_GIBBS = 2, MSPDE_STEP_SERIAL = 4 /* one stream, no task overlap */,
-       MSPDE_STEP_FAST_PHI = 8 /* determinant-lemma Phi (mspde_phi_fast) for both evaluations */ };
+       MSPDE_STEP_FAST_PHI = 8 /* determinant-lemma Phi (mspde_phi_fast) for both evaluations */,
+       MSPDE_STEP_NAIVE_PHI = 16 /* the reference's naive Phi (mspde_phi_naive) for both evaluations */ };
 
 /* out_dev (device, 4 doubles) <- {accepted (0/1), logRatio, Phi_cur, Phi_new}; record_dev (optional) <-
  * n_layers x n_ravel current half samples (Layer.record_sample, 792-795). */

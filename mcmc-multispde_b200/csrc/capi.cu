@@ -142,6 +142,8 @@ int mspde_ctx_destroy(mspde_ctx* h) {
         if (e) cudaEventDestroy(e);
     for (int s = 0; s < 2; ++s)
         if (h->c.pw[s].A) cudaFree(h->c.pw[s].A);
+    for (void* p : {(void*)h->c.naive_aug, h->c.naive_lu_work, (void*)h->c.naive_ut, (void*)h->c.naive_xy})
+        if (p) cudaFree(p);
     for (void* p : h->owned) cudaFree(p);
     delete h;
     return 0;
@@ -175,6 +177,7 @@ void* mspde_ctx_buffer(mspde_ctx* h, const char* name, int* ld) {
     if (!strcmp(name, "r")) { if (ld) *ld = c.ldN; return c.r; }
     if (!strcmp(name, "X")) { if (ld) *ld = c.ldM; return c.X; }
     if (!strcmp(name, "Q")) { if (ld) *ld = c.ldM; return c.Q; }
+    if (!strcmp(name, "Z")) { if (ld) *ld = (c.N + c.M + 7) / 8 * 8; return c.naive_aug ? c.naive_aug + c.N : nullptr; }
     if (!strcmp(name, "tp")) { if (ld) *ld = c.il; return c.tp; }
     if (!strcmp(name, "tm")) { if (ld) *ld = c.il; return c.tm; }
     if (!strcmp(name, "fp")) { if (ld) *ld = c.m; return c.fp; }
@@ -266,6 +269,10 @@ int mspde_pcn_step(mspde_ctx* h, const mspde_chain* chain, const mspde_step_nois
         return -1;
     }
     return pcn_step(&h->c, chain, noise, flags, out_dev, (cplx*)record_dev);
+}
+
+int mspde_phi_naive(mspde_ctx* h, const void* L, int ldl, double* out3_dev) {
+    return phi_eval_naive(&h->c, h->c.stream, h->c.pw[0], (const cplx*)L, ldl, out3_dev);
 }
 
 int mspde_phi_fast(mspde_ctx* h, const void* L, int ldl, double* out3_dev) {

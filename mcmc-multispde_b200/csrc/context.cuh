@@ -58,6 +58,10 @@ struct Ctx {
     void* lu_work = nullptr;
     cplx* vecN = nullptr;     // scratch vectors (4 x (N+M))
     cplx* gvec = nullptr;     // H^H y (fast Phi formulation)
+    cplx* naive_aug = nullptr;        // naive Phi variant: [L^H | H^H], N x (N+M); allocated on first use
+    void* naive_lu_work = nullptr;
+    cplx* naive_ut = nullptr;         // U^T
+    cplx* naive_xy = nullptr;         // C^-1 y
     bool g_valid = false;
 
     // side streams for the independent heavy tasks of one step (Phi(L_current), Gibbs QR) and their events
@@ -82,6 +86,7 @@ int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double
 int add_diag(cudaStream_t st, cplx* A, int lda, int n, double v);
 int upper_rows_times_y(cudaStream_t st, const cplx* V, int ldv, int nrows, int ncols, const double* y, double* rowsq,
                        double* rowlog);
+int phi_eval_naive(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3);
 int phi_fast_prepare(Ctx* c, cudaStream_t st);
 int phi_eval_fast(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3);   // out3 (device): phi, quad, logdet
 

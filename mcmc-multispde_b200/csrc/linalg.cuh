@@ -27,6 +27,10 @@ int lu_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int goff
 int lu_panel_apply(cudaStream_t st, int mp, int pw, int n, int ntot, void* work, cplx* A12, int lda, int n2);
 void lu_work_layout(int n, int ntot, void* work, long long* out6);
 
+// trsm_upper.cu
+int transpose(cudaStream_t st, const cplx* in, int ldi, int rows, int cols, bool conj, cplx* out, int ldo);
+int trsm_upper(cudaStream_t st, const cplx* U, int ldu, int n, cplx* B, int ldb, int ncols, cplx* Ut, int ldut, cplx* invT);
+
 // geqrf.cu
 size_t qr_work_bytes(int rows, int cols);
 // Householder QR of the leading `cols` columns of A (rows x (cols+naug), rows >= cols); the naug trailing columns

@@ -170,7 +170,8 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
         Ctx* c; cudaStream_t saved;
         ~StreamGuard() { c->stream = saved; }
     } guard{c, caller};
-    cudaStream_t s1 = serial ? st : c->s1, s2 = serial ? st : c->s2;
+    const bool naive = (flags & MSPDE_STEP_NAIVE_PHI) != 0;      // both evaluations share one LU workspace: same stream
+    cudaStream_t s1 = (serial || naive) ? st : c->s1, s2 = serial ? st : c->s2;
     if (flags & MSPDE_STEP_FAST_PHI) {
         int rc0 = phi_fast_prepare(c, caller);
         if (rc0) return rc0;
@@ -195,10 +196,11 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
     // ---- stream s1: Phi(L_current) only depends on the previous step (image_cupy.py:567-568)
     const bool cached = (flags & MSPDE_STEP_CACHE_PHI_CUR) && ch->phi_cur_valid;
     if (!cached) {
-        rc = fast ? phi_eval_fast(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3)
-                  : phi_eval(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3, serial);
+        rc = naive ? phi_eval_naive(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3)
+             : fast ? phi_eval_fast(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3)
+                    : phi_eval(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3, serial);
         if (rc) return rc;
-        if (!serial) MSPDE_CUDA(cudaEventRecord(c->ev_s1, s1));
+        if (!serial && !naive) MSPDE_CUDA(cudaEventRecord(c->ev_s1, s1));
     }
     // ---- main stream: layers 0..K-2 (557-564)
     for (int k = 0; k < K - 1; ++k) {
@@ -250,11 +252,12 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
         MSPDE_LAUNCH_CHECK();
     }
     // ---- main stream: Phi(L_latest) (571), then join
-    rc = fast ? phi_eval_fast(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3)
-              : phi_eval(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3, serial);
+    rc = naive ? phi_eval_naive(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3)
+         : fast ? phi_eval_fast(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3)
+                : phi_eval(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3, serial);
     if (rc) return rc;
     if (!serial) {
-        if (!cached) MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_s1, 0));
+        if (!cached && !naive) MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_s1, 0));
         if (do_gibbs) MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_s2, 0));
     }
     accept_kernel<<<1, 32, 0, st>>>(phi_cur3, phi_new3, nz->log_u, out_dev);                              // 573

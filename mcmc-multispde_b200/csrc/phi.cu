@@ -210,6 +210,61 @@ int phi_eval_fast(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, d
     return 0;
 }
 
+// out3 = {0.5*sum|x|^2 + sum log diag V, 0.5*sum|x|^2, sum log diag V}   (naive variant, image_cupy.py:657)
+__global__ void __launch_bounds__(1024) phi_naive_reduce_kernel(const cplx* __restrict__ x, const cplx* __restrict__ V, int ldv,
+                                                                int M, double* __restrict__ out3) {
+    __shared__ double s1[1024], s2[1024];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < M; i += 1024) {
+        const cplx xi = x[i];
+        a += xi.x * xi.x + xi.y * xi.y;
+        b += log(V[size_t(i) * ldv + i].x);
+    }
+    s1[threadIdx.x] = a; s2[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 512; o; o >>= 1) {
+        if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out3[0] = 0.5 * s1[0] + s2[0]; out3[1] = 0.5 * s1[0]; out3[2] = s2[0]; }
+}
+
+// "Naive" Phi of the reference (use_naive_logRatio_implementation, image_cupy.py:644-657), no stabiliser:
+//   Z = solve(L^H, H^H)  (pivoted LU of L^H with the M columns of H^H carried along, then U^-1 on all of them)
+//   C = chol(Z^H Z + I) ; Phi = 0.5 * || C^-1 y ||^2 + sum(log(Re diag C))
+int phi_eval_naive(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3) {
+    const int N = c->N, M = c->M;
+    const int ldz = (N + M + 7) / 8 * 8;
+    if (!c->naive_aug) {   // [L^H | H^H] workspace and its LU scratch, allocated on first use (freed with the context)
+        MSPDE_CUDA(cudaMalloc((void**)&c->naive_aug, size_t(N) * ldz * sizeof(cplx)));
+        MSPDE_CUDA(cudaMalloc((void**)&c->naive_lu_work, lu_work_bytes(N, N + M)));
+        MSPDE_CUDA(cudaMalloc((void**)&c->naive_ut, size_t(N) * c->ldN * sizeof(cplx)));
+        MSPDE_CUDA(cudaMalloc((void**)&c->naive_xy, size_t(M) * sizeof(cplx)));
+    }
+    cplx* A = c->naive_aug;
+    int rc = transpose(st, L, ldl, N, N, true, A, ldz);                                   // L^H
+    if (rc) return rc;
+    MSPDE_CUDA(cudaMemcpy2DAsync(A + N, size_t(ldz) * sizeof(cplx), c->Hct, size_t(c->ldHct) * sizeof(cplx),
+                                 size_t(M) * sizeof(cplx), N, cudaMemcpyDeviceToDevice, st));   // H^H
+    rc = getrf_aug(st, A, ldz, N, M, c->naive_lu_work, c->info, nullptr);
+    if (rc) return rc;
+    rc = trsm_upper(st, A, ldz, N, A + N, ldz, M, c->naive_ut, c->ldN, w.winv);            // Z (N x M) in the augmented block
+    if (rc) return rc;
+    rc = zgemm_tn(st, true, M, M, N, 1.0, A + N, ldz, A + N, ldz, 0.0, w.Q, c->ldM, GEMM_UPPER);   // Z^H Z
+    if (rc) return rc;
+    add_diag_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.Q, c->ldM, M, 1.0);
+    MSPDE_LAUNCH_CHECK();
+    rc = potrf_upper(st, w.Q, c->ldM, M, w.winv, c->info, nullptr);                       // Q = V^H V, C = V^H
+    if (rc) return rc;
+    real_to_cplx_kernel<<<(M + 255) / 256, 256, 0, st>>>(c->y, c->naive_xy, M);
+    MSPDE_LAUNCH_CHECK();
+    rc = trsm_uh(st, w.Q, c->ldM, w.winv, M, c->naive_xy, 1, 1);                          // x = C^-1 y = V^-H y
+    if (rc) return rc;
+    phi_naive_reduce_kernel<<<1, 1024, 0, st>>>(c->naive_xy, w.Q, c->ldM, M, out3);
+    MSPDE_LAUNCH_CHECK();
+    return 0;
+}
+
 int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double* out3, bool serial) {
     const int N = c->N, M = c->M;
     // r = HtH + delta I + L^H L (upper triangle)

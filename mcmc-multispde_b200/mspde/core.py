@@ -17,6 +17,7 @@ STEP_CACHE_PHI_CUR = 1
 STEP_SKIP_GIBBS = 2
 STEP_SERIAL = 4
 STEP_FAST_PHI = 8
+STEP_NAIVE_PHI = 16
 
 
 class _Chain(ctypes.Structure):
@@ -150,10 +151,11 @@ class MspdeContext:
                                               L.stride(0)), "construct_L")
         return L
 
-    def phi(self, L, parts: bool = False, fast: bool = False):
-        """Phi(L) of pCN._log_ratio; synchronises to return Python floats.  fast=True: determinant-lemma form."""
+    def phi(self, L, parts: bool = False, fast: bool = False, naive: bool = False):
+        """Phi(L) of pCN._log_ratio; synchronises to return Python floats.  fast=True: determinant-lemma form;
+        naive=True: the reference's naive branch (644-657, no stabiliser)."""
         self._sync_stream()
-        fn = self.lib.mspde_phi_fast if fast else self.lib.mspde_phi
+        fn = self.lib.mspde_phi_naive if naive else (self.lib.mspde_phi_fast if fast else self.lib.mspde_phi)
         _ffi.check(fn(self._h, _ffi.ptr(L), L.stride(0), _ffi.ptr(self.scal)), "phi")
         self.check_info("phi (Cholesky)")
         v = self.scal[:3].cpu().numpy()

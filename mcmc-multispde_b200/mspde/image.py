@@ -17,7 +17,8 @@ import numpy as np
 import torch
 
 from . import util
-from .core import CDTYPE, ChainBuffers, MspdeContext, STEP_CACHE_PHI_CUR, STEP_FAST_PHI, STEP_SKIP_GIBBS
+from .core import (CDTYPE, ChainBuffers, MspdeContext, STEP_CACHE_PHI_CUR, STEP_FAST_PHI, STEP_NAIVE_PHI,
+                   STEP_SKIP_GIBBS)
 
 ORDER = util.ORDER
 
@@ -364,9 +365,7 @@ class pCN:
     # -- Phi (618-662) -------------------------------------------------------------------------------------
     def _log_ratio(self, L):
         self._ensure_inputs()
-        if self.use_naive_logRatio_implementation:
-            raise NotImplementedError("naive Phi variant (644-657) is a SURVEY 8(f2) item, not built yet")
-        return self.ctx.phi(L, fast=self.fast_phi)
+        return self.ctx.phi(L, fast=self.fast_phi, naive=self.use_naive_logRatio_implementation)    # 633 / 644
 
     # -- one iteration (553-617) ---------------------------------------------------------------------------
     def _bind(self, Layers):
@@ -411,7 +410,7 @@ class pCN:
         cb = self._bind(Layers)
         w_half, log_u, w_last, e = noise if noise is not None else self._draw_noise()
         flags = ((STEP_CACHE_PHI_CUR if self.cache_phi_current else 0) | (STEP_SKIP_GIBBS if self.skip_gibbs else 0)
-                 | (STEP_FAST_PHI if self.fast_phi else 0))
+                 | (STEP_FAST_PHI if self.fast_phi else 0) | (STEP_NAIVE_PHI if self.use_naive_logRatio_implementation else 0))
         do_record = (self.record_count % self.record_skip) == 0
         rec = self._record_buffer(Layers) if do_record else None
         self.ctx.pcn_step(cb, w_half, log_u, w_last, e, flags=flags, record=rec, out=self._out)

@@ -60,8 +60,6 @@ def main(argv=None):
     args = parser.parse_args(argv)
     if args.n_theta == 18:                      # twoDsim.py:98-99
         args.seed = 2
-    if args.naive:
-        raise NotImplementedError("--naive (image_cupy.py:644-657) is not built; --fast-phi style reformulations are opt-in on pCN")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     sim = im.Simulation(n_layers=args.n_layers, n_samples=args.n_samples, n=args.n, n_extended=args.n_extended, beta=args.beta,
                         kappa=args.kappa, sigma_0=args.sigma_0, sigma_v=args.sigma_v, sigma_scaling=args.sigma_scaling,
@@ -73,6 +71,7 @@ def main(argv=None):
     sim.pcn.set_chol_epsilon(args.chol_epsilon)                 # twoDsim.py:106
     sim.pcn.target_acceptance_rate = 0.234                      # twoDsim.py:107
     sim.pcn.use_beta_adaptation = args.adapt_sqrtbeta           # twoDsim.py:108
+    sim.pcn.use_naive_logRatio_implementation = args.naive      # twoDsim.py:109
     parent = pathlib.Path(args.result_dir) if args.result_dir else pathlib.Path.cwd() / 'SimulationResult'
     folder = parent / ('result-' + datetime.datetime.now().strftime('%d-%b-%Y_%H_%M_%S') if args.seq_no == 0 else args.init_folder)
     folder.mkdir(parents=True, exist_ok=True)

@@ -251,6 +251,37 @@ def test_fast_phi_matches_woodbury(toy, full):
     assert abs(a[0] - b[0]) <= RTOL * abs(a[0]), (a, b)
 
 
+def test_naive_phi_variant(toy, full):
+    """f2: the reference's naive Phi branch (image_cupy.py:644-657) -- LU of L^H with M right-hand sides, multi-RHS upper
+    solve, Cholesky of Z^H Z + I.  Z = solve(L^H, H^H) is checked at 1e-10 x cond(L); Phi itself only to 1e-7: without the
+    stabiliser Q = I + Z^H Z is so ill-conditioned that the oracle's own three formulas agree to ~1e-9 only
+    (tests/test_oracle_pins.py).  At full size the multi-right-hand-side solve is checked through its residual."""
+    hp, pb, pt, ns, st, ctx = toy
+    N, M = pb["ft"].N, pb["H"].shape[0]
+    for k in (1, 2):
+        L = st.L_cur[k]
+        Ld = ctx.new_matrix(N, N); Ld.copy_(ctx.to_dev(L))
+        try:
+            pn = ctx.phi(Ld, parts=True, naive=True)
+        except np.linalg.LinAlgError:
+            # cond(L) ~ 5e9 for the last toy layer: I + Z^H Z is numerically indefinite, the reference's own Cholesky at
+            # line 656 fails the same way (that is why its default is the stabilised Woodbury form)
+            assert k == 2
+            pn = None
+        Zo = np.linalg.solve(L.conj().T, pb["H"].conj().T)
+        assert rel(ctx.buffer("Z", N, M).cpu(), Zo) <= 1e-13 * np.linalg.cond(L)
+        if k == 1:
+            po = o.phi_naive(L, pb["H"], pb["y"], 0.0)
+            assert abs(pn[0] - po) <= 1e-7 * abs(po), (pn, po)
+    c2 = full.pcn.ctx
+    L = full.Layers[2].LMat.current_L
+    b = c2.phi(L, naive=True)       # differs from the Woodbury value by the effect of delta on the near-null space of L
+    assert np.isfinite(b)
+    Z = c2.buffer("Z", c2.N, c2.M)
+    resid = L.contiguous().conj().T @ Z - c2.Hct
+    assert float(resid.abs().max()) <= 1e-9 * float(c2.Hct.abs().max()) * 1e3
+
+
 def _load_chain(ctx, st):
     from mspde.core import ChainBuffers
     K = len(st.noise_cur)
