@@ -206,6 +206,50 @@ def test_field_coeffs_and_L_vs_oracle(toy):
         assert rel(Le, st.L_cur[k]) < RTOL
 
 
+@pytest.mark.parametrize("n,n_ext", [(4, 4), (4, 6), (5, 9), (8, 8)])
+def test_assembly_other_paddings(n, n_ext):
+    """extend2D is a no-op for n_ext = n and pads to m = 2 n_ext - 1 otherwise (util_cupy.py:251-267): other image sizes."""
+    from mspde.core import MspdeContext
+    ft = o.FourierTables(n, n_ext)
+    ctx = MspdeContext(n, n_ext, 16, 2)
+    N = ft.N
+    ctx.set_inputs(np.zeros((16, N), np.complex128), np.zeros((N, N), np.complex128), np.zeros(16), ft.D_diag, np.ones(N), 0.0)
+    rng = np.random.default_rng(n * 10 + n_ext)
+    u = o.symmetrize(o.w_half_from_normals(rng.standard_normal(ft.n_ravel), rng.standard_normal(ft.n_ravel))) * 2.0
+    tp, tm = o.field_coeffs(u, ft)
+    tpd, tmd = ctx.field_coeffs(ctx.to_dev(u))
+    assert rel(tpd.cpu(), tp) < RTOL and rel(tmd.cpu(), tm) < RTOL
+    assert rel(ctx.construct_L(ctx.to_dev(u), 3.0).cpu(), o.assemble_L(u, 3.0, ft)) < RTOL
+    ctx.close()
+
+
+def test_four_layer_chain_vs_oracle():
+    """n_layers = 4: two non-stationary middle layers (two assemblies + two dense solves before the last layer)."""
+    from mspde.core import MspdeContext
+    hp = o.Hyper(n_layers=4, n=4, n_ext=64, n_theta=8, beta=0.4, sigma_scaling=1e-3)   # default 0.4 overflows exp() four layers deep at this toy size
+    pb = o.synthetic_problem(hp)
+    ft, H, HtH, y, delta = pb["ft"], pb["H"], pb["HtH"], pb["y"], pb["delta"]
+    pt = o.prior_tables(hp, ft)
+    K, M = 4, H.shape[0]
+    ns = o.NoiseStream(5, K, ft.n_ravel, M)
+    st = o.init_chain(hp, ft, [ns.half() for _ in range(K)], [ns.half() for _ in range(K)])
+    ctx = MspdeContext(4, 64, M, K)
+    ctx.set_inputs(H, HtH, y, ft.D_diag, pt["stdev_sym"], delta)
+    cb = _load_chain(ctx, st)
+    rec = torch.zeros((K, ft.n_ravel), dtype=torch.complex128, device=ctx.device)
+    for it in range(4):
+        nz = ns.draw_iteration()
+        d = o.one_step(st, ft, H, HtH, y, delta, nz)
+        out = ctx.pcn_step(cb, [ctx.to_dev(w) for w in nz["w_half"]], nz["log_u"], ctx.to_dev(nz["w_last"]), ctx.to_dev(nz["e"]),
+                           record=rec).cpu().numpy()
+        ctx.check_info("step")
+        assert int(out[0]) == int(d["accepted"])
+        assert abs(out[2] - d["phi_cur"]) <= RTOL * abs(d["phi_cur"]) and abs(out[3] - d["phi_new"]) <= RTOL * abs(d["phi_new"])
+        for k in range(K):
+            assert rel(cb.u_new[k].cpu(), st.u_new_sym[k]) < 1e-9
+    ctx.close()
+
+
 def test_phi_solve_lstsq_vs_oracle(toy):
     hp, pb, pt, ns, st, ctx = toy
     ft, H, HtH, y, delta = pb["ft"], pb["H"], pb["HtH"], pb["y"], pb["delta"]
