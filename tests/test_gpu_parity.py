@@ -63,6 +63,30 @@ def test_zgemm_tn_matches_cublas(lib, m, n, k, conj, uplo, beta):
         assert rel(C.cpu(), ref.cpu()) < 1e-13
 
 
+def test_zgemm_tn_random_shapes_and_views(lib):
+    """40 random (m, n, k) including tiny and non-multiple-of-tile sizes, operands as strided sub-views (the factorizations
+    call the kernel on sub-blocks), guard values around C to catch any out-of-bounds store."""
+    rng = np.random.default_rng(1234)
+    for trial in range(40):
+        m, n, k = (int(rng.integers(1, 200)) for _ in range(3))
+        if trial % 5 == 0:
+            k = int(rng.integers(1, 40))
+        conj, beta = bool(rng.integers(0, 2)), float(rng.choice([0.0, 1.0, -0.5]))
+        pad = 3
+        Abig = crandn(k + 2 * pad, m + 2 * pad + 5, seed=trial)
+        Bbig = crandn(k + 2 * pad, n + 2 * pad + 1, seed=trial + 100)
+        Cbig = crandn(m + 2 * pad, n + 2 * pad + 7, seed=trial + 200)
+        A, B, C = Abig[pad:pad + k, pad:pad + m], Bbig[pad:pad + k, pad:pad + n], Cbig[pad:pad + m, pad:pad + n]
+        C0 = Cbig.clone()
+        ref = 0.75 * ((A.conj().T if conj else A.T) @ B) + beta * C
+        _gemm(lib, A, B, C, conj, 0.75, beta, 0)
+        torch.cuda.synchronize()
+        assert rel(C.cpu(), ref.cpu()) < 1e-13, (trial, m, n, k)
+        guard = torch.ones_like(Cbig, dtype=torch.bool)
+        guard[pad:pad + m, pad:pad + n] = False
+        assert torch.equal(Cbig[guard], C0[guard]), (trial, m, n, k)       # nothing written outside the m x n block
+
+
 def test_zgemm_tn_splitk_deterministic(lib):
     A, B = crandn(3001, 64, seed=4), crandn(3001, 500, seed=5)
     ws = torch.empty(8 * 64 * 500, dtype=torch.complex128, device="cuda")
