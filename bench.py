@@ -198,6 +198,8 @@ def main():
         sampler.start()
         runs = [stp.run_overlapped() for _ in range(args.steps)]
         clocks = sampler.stop()
+        stp.verify = True                      # one extra, untimed iteration with residual checks
+        checks = stp.run_overlapped()["checks"]
         sec = sum(r["seconds"] for r in runs) / len(runs)
         if rank == 0:
             print(json.dumps({"metric": "pCN iters/sec (n=96, 3 layers, one chain block-distributed)", "value": 1.0 / sec,
@@ -209,7 +211,8 @@ def main():
                               "roofline": {"bound": "tensor", "achieved": f_iter / sec / 1e12 / world, "peak": FP64_PEAK_TFLOPS,
                                            "unit": "TFLOP/s per GPU", "frac": f_iter / sec / 1e12 / world / FP64_PEAK_TFLOPS,
                                            "aggregate_tflops": f_iter / sec / 1e12, "traffic": None},
-                              "clocks": clocks, "finite": all(r["finite"] for r in runs)}))
+                              "clocks": clocks, "finite": all(r["finite"] for r in runs), "residual_checks": checks,
+                              "phi_latest": runs[-1]["phi"]}))
         dist.destroy_process_group()
         return
     K = cfg["n_layers"]
