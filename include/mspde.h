@@ -23,6 +23,16 @@ typedef struct mspde_ctx mspde_ctx;
 const char* mspde_last_error(void);
 long long mspde_launch_count(void);   /* kernels launched by the library so far (bench.py gpu_launches) */
 
+/* Complex product scheme of every dense contraction of the path (the cuBLAS ZGEMM calls behind `@`, cp.linalg.solve,
+ * cp.linalg.cholesky and util.lstsq: mcmc/image_cupy.py:561, 634-643; mcmc/util_cupy.py:590-609).
+ *   MSPDE_GEMM_4M: four real products per complex product, 8 flop per multiply-add (what ZGEMM does);
+ *   MSPDE_GEMM_3M: three real products (T1 = ArBr, T2 = AiBi, T3 = (Ar+Ai)(Br+Bi)), 6 flop -- the ZGEMM3M scheme; normwise
+ *                  the same O(u) error bound, 1.2x the throughput on the FP64 tensor pipe.  Default.
+ * Process-wide; also selectable with the environment variable MSPDE_GEMM=3m|4m before the first launch. */
+enum { MSPDE_GEMM_4M = 0, MSPDE_GEMM_3M = 1 };
+int mspde_set_gemm_mode(int mode);
+int mspde_get_gemm_mode(void);
+
 /* Context = sizes + borrowed fixed inputs + library-owned workspace (replaces the managed-memory pool and the
  * temporaries of pCN._log_ratio, mcmc/image_cupy.py:834-835, 634-643). */
 int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n_layers, void* stream);

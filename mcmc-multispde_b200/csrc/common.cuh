@@ -72,6 +72,11 @@ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
 
 // ---- GEMM (zgemm_tn.cu) --------------------------------------------------------------------------
 enum { GEMM_FULL = 0, GEMM_UPPER = 1 };
+// Complex product scheme of every GEMM launch: 4M = four real products (8 flop per complex multiply-add), 3M = three real
+// products (6 flop, the ZGEMM3M scheme).  Process-wide; chosen by mspde_set_gemm_mode() or MSPDE_GEMM=3m|4m.
+enum { GEMM_4M = 0, GEMM_3M = 1, GEMM_DEFAULT_MODE = GEMM_3M };
+int gemm_mode();
+int set_gemm_mode(int mode);
 // C[i][j] = alpha * sum_k opA(A[k][i]) * B[k][j] + beta * C[i][j];  A: k x m, B: k x n, C: m x n, row-major.
 int zgemm_tn(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, const cplx* A, int lda,
              const cplx* B, int ldb, double beta, cplx* C, int ldc, int uplo);

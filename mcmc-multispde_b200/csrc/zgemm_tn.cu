@@ -227,6 +227,202 @@ __global__ void __launch_bounds__(THREADS, 2) zgemm_tn_kernel(GemmArgs p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// 3M variant (opt-in, MSPDE_GEMM_3M=1): three real products per complex product instead of four,
+//     T1 = Ar^T Br,  T2 = Ai^T Bi,  T3 = (Ar +- Ai)^T (Br + Bi)
+//     plain: C = (T1 - T2) + i (T3 - T1 - T2)        conj(A): C = (T1 + T2) + i (T3 - T1 + T2)   [T3 built with Ar - Ai]
+// so the FP64 tensor pipe executes 6 instead of 8 real flops per complex multiply-add (cuBLAS calls the same scheme
+// ZGEMM3M).  Normwise the rounding error stays O(u) * sum |a||b|; the imaginary part loses the componentwise bound of the
+// 4M form, which is why this is an option measured beside the default and not the default itself.
+// One DMMA.8x8x4 is a real 8 x 8 x 4 product here: a lane loads one complex A element (k = t, row g) and one complex B
+// element (k = t, col g) with a 128-bit shared-memory load and feeds re, im and re+-im to the three accumulator sets.
+// Three accumulator sets cost 1.5x the registers, so the CTA tile is 64 x 32 (8 MMA warps of 16 x 16), still 2 CTAs/SM.
+template <int BN_, int STAGES_>
+struct M3 {
+    static constexpr int BM = 64, BN = BN_, BK = 16, STAGES = STAGES_;
+    static constexpr int PA = BM + 2;   // pitch == 2 mod 8 (complex): the 8 lanes of a 128-bit quarter-warp load hit 8 distinct 16 B slots
+    static constexpr int PB = BN + 2;
+    static constexpr int WARPS = 4 * (BN / 16);          // MMA warps: 4 along i x BN/16 along j, 16 x 16 each
+    static constexpr int NTHREADS = (WARPS + 1) * 32;
+    static constexpr int STAGE_DOUBLES = (BK * PA + BK * PB) * 2;
+    static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+};
+typedef M3<32, 4> M3N;    // 64 x 32 tile, 288 threads, 2 CTAs/SM.  (A 64 x 64 tile with 16 MMA warps at 1 CTA/SM measured 2-25 % slower.)
+
+template <class T>
+__global__ void __launch_bounds__(T::NTHREADS, T::BN == 32 ? 2 : 1) zgemm3m_tn_kernel(GemmArgs p) {
+    constexpr int BM = T::BM, BN = T::BN, BK = T::BK, STAGES = T::STAGES, PA = T::PA, PB = T::PB;
+    constexpr int STAGE_DOUBLES = T::STAGE_DOUBLES;
+    constexpr int CONSUMER_WARPS = T::WARPS;
+    const int tiles_i = (p.m + BM - 1) / BM, tiles_j = (p.n + BN - 1) / BN;
+    const int pid = blockIdx.x;
+    const int per_group = GROUP_I * tiles_j;
+    const int first_i = (pid / per_group) * GROUP_I;
+    const int gsize = min(tiles_i - first_i, GROUP_I);
+    const int i0 = (first_i + (pid % per_group) % gsize) * BM;
+    const int j0 = ((pid % per_group) / gsize) * BN;
+    if (p.uplo == GEMM_UPPER && j0 + BN - 1 < i0) return;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage_base = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + size_t(STAGES) * STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty_bar = full_bar + STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    const int kbeg = blockIdx.z * p.kslice;
+    const int kend = min(p.k, kbeg + p.kslice);
+    const int klen = kend - kbeg;
+    const int ktiles = (klen + BK - 1) / BK;
+    cplx* __restrict__ C = p.C + size_t(blockIdx.z) * p.cslice;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int mrows = min(BM, p.m - i0);
+    const int ncols = min(BN, p.n - j0);
+
+    if (warp == CONSUMER_WARPS) {
+        const bool isA = lane < BK;
+        const int r = isA ? lane : lane - BK;
+        const cplx* src_base = isA ? (p.A + size_t(kbeg) * p.lda + i0) : (p.B + size_t(kbeg) * p.ldb + j0);
+        const size_t ld = isA ? p.lda : p.ldb;
+        const uint32_t row_bytes = uint32_t(isA ? mrows : ncols) * 16u;
+        const int dst_off = isA ? r * PA * 2 : (BK * PA + r * PB) * 2;
+        int stage = 0;
+        uint32_t parity = 0;
+        for (int kt = 0; kt < ktiles; ++kt) {
+            mbar_wait(&empty_bar[stage], parity ^ 1);
+            const int kvalid = min(BK, klen - kt * BK);
+            if (lane == 0) mbar_expect_tx(&full_bar[stage], uint32_t(kvalid) * uint32_t(mrows + ncols) * 16u);
+            __syncwarp();
+            if (r < kvalid) {
+                bulk_g2s(stage_base + size_t(stage) * STAGE_DOUBLES + dst_off, src_base + (size_t(kt) * BK + r) * ld,
+                         row_bytes, &full_bar[stage]);
+            }
+            if (++stage == STAGES) { stage = 0; parity ^= 1; }
+        }
+        return;
+    }
+
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int wi = warp & 3;          // 4 warps along i (16 rows each)
+    const int wj = warp >> 2;         // 2 warps along j (16 complex cols each)
+    const int a_off = (t * PA + wi * 16 + g) * 2;                 // doubles; + kk*4*PA*2 per k4 step, + 16 per fragment
+    const int b_off = (BK * PA + t * PB + wj * 16 + g) * 2;
+    const bool conj = p.conjA != 0;
+    const double csign = conj ? -1.0 : 1.0;      // A enters T3 as Ar + csign * Ai
+
+    double t1[2][2][2], t2[2][2][2], t3[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) t1[a][b][c] = t2[a][b][c] = t3[a][b][c] = 0.0;
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int kt = 0; kt < ktiles; ++kt) {
+        mbar_wait(&full_bar[stage], parity);
+        const double* S = stage_base + size_t(stage) * STAGE_DOUBLES;
+        const int kvalid = klen - kt * BK;
+        if (kvalid >= BK) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                double2 av[2], bv[2];
+                double as[2], bs[2];
+#pragma unroll
+                for (int a = 0; a < 2; ++a) av[a] = *reinterpret_cast<const double2*>(S + a_off + kk * 4 * PA * 2 + a * 16);
+#pragma unroll
+                for (int b = 0; b < 2; ++b) bv[b] = *reinterpret_cast<const double2*>(S + b_off + kk * 4 * PB * 2 + b * 16);
+                as[0] = fma(csign, av[0].y, av[0].x);
+                as[1] = fma(csign, av[1].y, av[1].x);
+                bs[0] = bv[0].x + bv[0].y;
+                bs[1] = bv[1].x + bv[1].y;
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) dmma884(t1[a][b][0], t1[a][b][1], av[a].x, bv[b].x);
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) dmma884(t2[a][b][0], t2[a][b][1], av[a].y, bv[b].y);
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) dmma884(t3[a][b][0], t3[a][b][1], as[a], bs[b]);
+            }
+        } else {
+            // k tail: rows >= kvalid of the stage were not fetched; feed zeros for them
+            const int nk4 = (kvalid + 3) >> 2;
+            for (int kk = 0; kk < nk4; ++kk) {
+                const bool dead = (kk * 4 + t) >= kvalid;
+                double2 av[2], bv[2];
+                double as[2], bs[2];
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    av[a] = dead ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(S + a_off + kk * 4 * PA * 2 + a * 16);
+                    as[a] = fma(csign, av[a].y, av[a].x);
+                }
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    bv[b] = dead ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(S + b_off + kk * 4 * PB * 2 + b * 16);
+                    bs[b] = bv[b].x + bv[b].y;
+                }
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        dmma884(t1[a][b][0], t1[a][b][1], av[a].x, bv[b].x);
+                        dmma884(t2[a][b][0], t2[a][b][1], av[a].y, bv[b].y);
+                        dmma884(t3[a][b][0], t3[a][b][1], as[a], bs[b]);
+                    }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; parity ^= 1; }
+    }
+
+    // epilogue: the accumulator fragment (row g, cols 2t, 2t+1) is two adjacent complex C elements
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int i = i0 + wi * 16 + a * 8 + g;
+        if (i >= p.m) continue;
+        cplx* crow = C + size_t(i) * p.ldc;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int j = j0 + wj * 16 + b * 8 + 2 * t + c;
+                if (j >= p.n) continue;
+                if (p.uplo == GEMM_UPPER && j < i) continue;
+                const double x1 = t1[a][b][c], x2 = t2[a][b][c], x3 = t3[a][b][c];
+                const double re = conj ? x1 + x2 : x1 - x2;
+                const double im = conj ? (x3 - x1) + x2 : (x3 - x1) - x2;
+                cplx out = make_double2(alpha * re, alpha * im);
+                if (beta != 0.0) {
+                    cplx cv = crow[j];
+                    out.x = fma(beta, cv.x, out.x);
+                    out.y = fma(beta, cv.y, out.y);
+                }
+                crow[j] = out;
+            }
+        }
+    }
+}
+
 __global__ void splitk_reduce_kernel(const cplx* __restrict__ part, int nsplit, long long slice, int m, int n,
                                      double alpha, double beta, cplx* __restrict__ C, int ldc) {
     long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -265,19 +461,41 @@ bool g_attr_set = false;
 
 int launch(cudaStream_t st, const GemmArgs& a, int nz) {
     if (a.m <= 0 || a.n <= 0) return 0;
+    const bool use3m = gemm_mode() == GEMM_3M;
     if (!g_attr_set) {
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        MSPDE_CUDA(cudaFuncSetAttribute(zgemm3m_tn_kernel<M3N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3N::SMEM_BYTES));
         g_attr_set = true;
     }
     static FILE* logf = getenv("MSPDE_GEMM_LOG") ? fopen(getenv("MSPDE_GEMM_LOG"), "w") : nullptr;   // dev aid: shapes per launch
     if (logf) { fprintf(logf, "%d %d %d %d %d\n", a.m, a.n, a.k, a.uplo, nz); fflush(logf); }
-    dim3 grid(((a.m + BM - 1) / BM) * ((a.n + BN - 1) / BN), 1, nz);
-    zgemm_tn_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    if (use3m) {
+        dim3 grid(((a.m + M3N::BM - 1) / M3N::BM) * ((a.n + M3N::BN - 1) / M3N::BN), 1, nz);
+        zgemm3m_tn_kernel<M3N><<<grid, M3N::NTHREADS, M3N::SMEM_BYTES, st>>>(a);
+    } else {
+        dim3 grid(((a.m + BM - 1) / BM) * ((a.n + BN - 1) / BN), 1, nz);
+        zgemm_tn_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(a);
+    }
     MSPDE_LAUNCH_CHECK();
     return 0;
 }
 
+int g_gemm_mode = -1;   // -1: not chosen yet (environment MSPDE_GEMM = 3m | 4m, else the default)
+
 }  // namespace
+
+int gemm_mode() {
+    if (g_gemm_mode < 0) {
+        const char* e = getenv("MSPDE_GEMM");
+        g_gemm_mode = (e && (e[0] == '4')) ? GEMM_4M : (e && (e[0] == '3')) ? GEMM_3M : GEMM_DEFAULT_MODE;
+    }
+    return g_gemm_mode;
+}
+int set_gemm_mode(int mode) {
+    if (mode != GEMM_4M && mode != GEMM_3M) { set_error("gemm mode must be 0 (4M) or 1 (3M)"); return -1; }
+    g_gemm_mode = mode;
+    return 0;
+}
 
 int zgemm_tn(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, const cplx* A, int lda, const cplx* B,
              int ldb, double beta, cplx* C, int ldc, int uplo) {

@@ -51,3 +51,15 @@ def ptr(t) -> ctypes.c_void_p:
 def current_stream() -> ctypes.c_void_p:
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+GEMM_4M, GEMM_3M = 0, 1
+
+
+def set_gemm_mode(mode: int):
+    """Process-wide complex product scheme of the GEMM kernel (include/mspde.h: MSPDE_GEMM_4M / MSPDE_GEMM_3M)."""
+    check(lib().mspde_set_gemm_mode(int(mode)), "set_gemm_mode")
+
+
+def get_gemm_mode() -> int:
+    return int(lib().mspde_get_gemm_mode())

@@ -42,11 +42,21 @@ def crandn(*shape, seed=0):
                          torch.randn(*shape, dtype=torch.float64, device="cuda", generator=g))
 
 
+@pytest.fixture(params=[0, 1], ids=["4M", "3M"])
+def gemm_mode(request):
+    """Runs a test under both complex product schemes of the GEMM kernel (include/mspde.h: mspde_set_gemm_mode)."""
+    from mspde import _ffi
+    default = _ffi.get_gemm_mode()
+    _ffi.set_gemm_mode(request.param)
+    yield request.param
+    _ffi.set_gemm_mode(default)
+
+
 # ------------------------------------------------------------------------------------------------ building blocks
 @pytest.mark.parametrize("m,n,k,conj,uplo,beta", [(64, 64, 16, 1, 0, 0.0), (1, 1, 1, 1, 0, 0.0), (100, 77, 35, 0, 0, 0.0),
                                                  (200, 130, 129, 1, 0, 1.0), (333, 333, 211, 1, 1, 1.0), (49, 1016, 49, 1, 0, -1.0),
                                                  (961, 961, 961, 1, 1, 0.0), (65, 63, 1, 1, 0, 0.0)])
-def test_zgemm_tn_matches_cublas(lib, m, n, k, conj, uplo, beta):
+def test_zgemm_tn_matches_cublas(lib, gemm_mode, m, n, k, conj, uplo, beta):
     A = crandn(k, m, seed=1)
     B = A if uplo else crandn(k, n, seed=2)
     C = crandn(m, n, seed=3)
@@ -63,7 +73,7 @@ def test_zgemm_tn_matches_cublas(lib, m, n, k, conj, uplo, beta):
         assert rel(C.cpu(), ref.cpu()) < 1e-13
 
 
-def test_zgemm_tn_random_shapes_and_views(lib):
+def test_zgemm_tn_random_shapes_and_views(lib, gemm_mode):
     """40 random (m, n, k) including tiny and non-multiple-of-tile sizes, operands as strided sub-views (the factorizations
     call the kernel on sub-blocks), guard values around C to catch any out-of-bounds store."""
     rng = np.random.default_rng(1234)
@@ -87,7 +97,7 @@ def test_zgemm_tn_random_shapes_and_views(lib):
         assert torch.equal(Cbig[guard], C0[guard]), (trial, m, n, k)       # nothing written outside the m x n block
 
 
-def test_zgemm_tn_splitk_deterministic(lib):
+def test_zgemm_tn_splitk_deterministic(lib, gemm_mode):
     A, B = crandn(3001, 64, seed=4), crandn(3001, 500, seed=5)
     ws = torch.empty(8 * 64 * 500, dtype=torch.complex128, device="cuda")
     C1 = torch.zeros(64, 500, dtype=torch.complex128, device="cuda")
@@ -712,6 +722,39 @@ def test_full_size_steps_are_reproducible(full):
         res.append((out.cpu(), Layers[2]._u_new.clone().cpu(), Layers[1]._u_new.clone().cpu()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
     assert torch.isfinite(res[0][1].abs()).all()
+
+
+def test_full_size_step_3m_vs_4m(full):
+    """The same full-size pCN iteration under the two complex product schemes of the GEMM kernel (6-flop 3M, the default,
+    and 8-flop 4M): same accept decision, Phi values within 1e-10 relative, samples within the conditioning of the solves."""
+    from mspde import util, _ffi
+    pcn, ctx, Layers = full.pcn, full.pcn.ctx, full.Layers
+    rng = np.random.Generator(np.random.PCG64(5))
+    nr, M, K = ctx.n_ravel, ctx.M, 3
+    w = [ctx.to_dev(util.w_half_from_normals(rng.standard_normal(nr), rng.standard_normal(nr))) for _ in range(K - 1)]
+    wl = ctx.to_dev(util.w_half_from_normals(rng.standard_normal(nr), rng.standard_normal(nr)))
+    e = ctx.to_dev(rng.standard_normal(M))
+    snap = [(l._noise_cur.clone(), l._u_cur.clone()) for l in Layers]
+    default = _ffi.get_gemm_mode()
+    res = []
+    try:
+        for mode in (_ffi.GEMM_4M, _ffi.GEMM_3M):
+            _ffi.set_gemm_mode(mode)
+            for l, (a, b) in zip(Layers, snap):
+                l._noise_cur.copy_(a); l._u_cur.copy_(b)
+            cb = pcn._bind(Layers)
+            out = ctx.pcn_step(cb, w, -0.3, wl, e).clone()
+            ctx.check_info("step")
+            res.append((out.cpu().numpy(), Layers[2]._u_new.clone(), Layers[1]._u_new.clone()))
+    finally:
+        _ffi.set_gemm_mode(default)
+        for l, (a, b) in zip(Layers, snap):
+            l._noise_cur.copy_(a); l._u_cur.copy_(b)
+    (o4, v4, u4), (o3, v3, u3) = res
+    assert int(o4[0]) == int(o3[0])
+    assert abs(o4[2] - o3[2]) <= RTOL * abs(o4[2]) and abs(o4[3] - o3[3]) <= RTOL * abs(o4[3])
+    assert float((u3 - u4).abs().max()) <= 1e-9 * float(u4.abs().max())
+    assert float((v3 - v4).abs().max()) <= 1e-9 * float(v4.abs().max())
 
 
 def test_block_distributed_phi_matches_single_gpu(toy):
