@@ -38,6 +38,8 @@ struct mspde_ctx {
         h->owned.push_back((void*)h->c.field);                   \
     } while (0)
 
+static int g_qr_aux_prio = 0;
+
 extern "C" {
 
 const char* mspde_last_error(void) { return get_error(); }
@@ -99,7 +101,10 @@ int mspde_ctx_create_ex(mspde_ctx** out, int device, int n, int n_ext, int M, in
         int lo = 0, hi = 0;   // numerically lower = higher priority
         MSPDE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         const int mid = (hi + 1 <= lo) ? hi + 1 : lo;
-        auto lvl = [&](int k) { int p = hi + k; return p > lo ? lo : p; };   // k = 0 highest
+        int order[6] = {0, 1, 2, 3, 4, 0};   // s0, s2, aux(Phi latest), s1, aux(Phi current), aux(QR); 0 = highest
+        if (const char* e = getenv("MSPDE_PRIO")) sscanf(e, "%d,%d,%d,%d,%d,%d", &order[0], &order[1], &order[2], &order[3], &order[4], &order[5]);
+        auto lvl = [&](int k) { int p = hi + order[k]; return p > lo ? lo : p; };
+        g_qr_aux_prio = lvl(5);
         MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s0, cudaStreamNonBlocking, lvl(0)));    // solve -> Phi(latest): critical path
         MSPDE_CUDA(cudaStreamCreateWithPriority(&c.s2, cudaStreamNonBlocking, lvl(1)));    // Gibbs QR
         MSPDE_CUDA(cudaStreamCreateWithPriority(&c.pw[0].la.aux, cudaStreamNonBlocking, lvl(2)));   // trailing HERKs of Phi(latest)
@@ -125,6 +130,15 @@ int mspde_ctx_create_ex(mspde_ctx** out, int device, int n, int n_ext, int M, in
         if (dmalloc(&w, qr_work_bytes(M + N, N))) { mspde_ctx_destroy(h); return -1; }
         h->owned.push_back(w);
         c.qr_work = w;
+        unsigned char* wq = nullptr;          // second panel workspace + stream + events: look-ahead of the Gibbs QR
+        if (dmalloc(&wq, qr_work_bytes(M + N, N))) { mspde_ctx_destroy(h); return -1; }
+        h->owned.push_back(wq);
+        c.qr_la.work2 = wq;
+        int lo = 0, hi = 0;
+        MSPDE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        MSPDE_CUDA(cudaStreamCreateWithPriority(&c.qr_la.aux, cudaStreamNonBlocking, g_qr_aux_prio));   // panel kernels: latency-critical
+        MSPDE_CUDA(cudaEventCreateWithFlags(&c.qr_la.ev_a, cudaEventDisableTiming));
+        MSPDE_CUDA(cudaEventCreateWithFlags(&c.qr_la.ev_b, cudaEventDisableTiming));
         unsigned char* w2 = nullptr;
         if (dmalloc(&w2, lu_work_bytes(N, N + 2))) { mspde_ctx_destroy(h); return -1; }
         h->owned.push_back(w2);
@@ -140,8 +154,11 @@ int mspde_ctx_destroy(mspde_ctx* h) {
     if (h->c.ev_out) cudaEventDestroy(h->c.ev_out);
     if (h->c.s1) cudaStreamDestroy(h->c.s1);
     if (h->c.s2) cudaStreamDestroy(h->c.s2);
-    for (cudaEvent_t e : {h->c.ev_start, h->c.ev_L, h->c.ev_s1, h->c.ev_s2})
+    for (cudaEvent_t e : {h->c.ev_start, h->c.ev_L, h->c.ev_s1, h->c.ev_s2, h->c.qr_la.ev_a, h->c.qr_la.ev_b,
+                          h->c.pw[0].la.ev_a, h->c.pw[0].la.ev_b, h->c.pw[1].la.ev_a, h->c.pw[1].la.ev_b})
         if (e) cudaEventDestroy(e);
+    for (cudaStream_t q : {h->c.qr_la.aux, h->c.pw[0].la.aux, h->c.pw[1].la.aux})
+        if (q) cudaStreamDestroy(q);
     for (int s = 0; s < 2; ++s)
         if (h->c.pw[s].A) cudaFree(h->c.pw[s].A);
     for (void* p : {(void*)h->c.naive_aug, h->c.naive_lu_work, (void*)h->c.naive_ut, (void*)h->c.naive_xy})

@@ -55,6 +55,7 @@ struct Ctx {
     cplx* QRaug = nullptr;    // (M+N) x ldA,  ldA = round8(N+1)
     int ldA = 0;
     void* qr_work = nullptr;
+    QrLookAhead qr_la;        // look-ahead of the Householder QR (second panel workspace, stream, events)
     void* lu_work = nullptr;
     cplx* vecN = nullptr;     // scratch vectors (4 x (N+M))
     cplx* gvec = nullptr;     // H^H y (fast Phi formulation)

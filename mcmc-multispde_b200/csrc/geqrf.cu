@@ -417,17 +417,49 @@ void qr_work_layout(int rows, int cols, void* work, long long* out6) {
 
 // Householder QR of the leading `cols` columns of Aaug (rows x (cols + naug)), trailing columns get Q^H applied.
 // logabs (device, optional) accumulates sum log |r_jj|.
-int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs) {
+int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs,
+              const QrLookAhead* la) {
     if (logabs) MSPDE_CUDA(cudaMemsetAsync(logabs, 0, sizeof(double), st));
     const int ntot = cols + naug;
-    for (int c0 = 0; c0 < cols; c0 += PW) {
+    if (la == nullptr || la->work2 == nullptr || cols <= PW) {
+        for (int c0 = 0; c0 < cols; c0 += PW) {
+            const int pw = min(PW, cols - c0);
+            const int mp = rows - c0;
+            cplx* Ap = A + size_t(c0) * lda + c0;
+            int rc = qr_panel_factor(st, Ap, lda, mp, pw, rows, cols, work, logabs);
+            if (rc) return rc;
+            rc = qr_panel_apply(st, mp, rows, cols, work, Ap + pw, lda, ntot - (c0 + pw));
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    // One-panel look-ahead: reflector p goes to the next panel's 64 columns first; the latency-bound factorisation of panel
+    // p+1 then runs on the auxiliary stream (into the other workspace) underneath the trailing update with reflector p.
+    void* wk[2] = {work, la->work2};
+    int rc = qr_panel_factor(st, A, lda, rows, min(PW, cols), rows, cols, wk[0], logabs);
+    if (rc) return rc;
+    int p = 0;
+    for (int c0 = 0; c0 < cols; c0 += PW, ++p) {
         const int pw = min(PW, cols - c0);
         const int mp = rows - c0;
         cplx* Ap = A + size_t(c0) * lda + c0;
-        int rc = qr_panel_factor(st, Ap, lda, mp, pw, rows, cols, work, logabs);
-        if (rc) return rc;
-        rc = qr_panel_apply(st, mp, rows, cols, work, Ap + pw, lda, ntot - (c0 + pw));
-        if (rc) return rc;
+        const int next = c0 + pw;
+        if (next < cols) {
+            const int pwn = min(PW, cols - next);
+            rc = qr_panel_apply(st, mp, rows, cols, wk[p & 1], Ap + pw, lda, pwn);
+            if (rc) return rc;
+            MSPDE_CUDA(cudaEventRecord(la->ev_a, st));
+            MSPDE_CUDA(cudaStreamWaitEvent(la->aux, la->ev_a, 0));
+            rc = qr_panel_factor(la->aux, A + size_t(next) * lda + next, lda, rows - next, pwn, rows, cols, wk[(p + 1) & 1], logabs);
+            if (rc) return rc;
+            MSPDE_CUDA(cudaEventRecord(la->ev_b, la->aux));
+            rc = qr_panel_apply(st, mp, rows, cols, wk[p & 1], Ap + pw + pwn, lda, ntot - (next + pwn));
+            if (rc) return rc;
+            MSPDE_CUDA(cudaStreamWaitEvent(st, la->ev_b, 0));
+        } else {
+            rc = qr_panel_apply(st, mp, rows, cols, wk[p & 1], Ap + pw, lda, ntot - next);
+            if (rc) return rc;
+        }
     }
     return 0;
 }
@@ -447,8 +479,9 @@ int trsv_upper_aug(cudaStream_t st, cplx* A, int lda, int n, int dcol, cplx* x) 
     return 0;
 }
 
-int lstsq_qr_aug(cudaStream_t st, cplx* Aaug, int lda, int rows, int cols, void* work, cplx* x, double* logabs) {
-    int rc = geqrf_aug(st, Aaug, lda, rows, cols, 1, work, logabs);
+int lstsq_qr_aug(cudaStream_t st, cplx* Aaug, int lda, int rows, int cols, void* work, cplx* x, double* logabs,
+                 const QrLookAhead* la) {
+    int rc = geqrf_aug(st, Aaug, lda, rows, cols, 1, work, logabs, la);
     if (rc) return rc;
     return trsv_upper_aug(st, Aaug, lda, cols, cols, x);
 }

@@ -35,13 +35,20 @@ int trsm_upper(cudaStream_t st, const cplx* U, int ldu, int n, cplx* B, int ldb,
 size_t qr_work_bytes(int rows, int cols);
 // Householder QR of the leading `cols` columns of A (rows x (cols+naug), rows >= cols); the naug trailing columns
 // receive Q^H applied.  logabs (device, optional) <- sum_j log|r_jj|.
-int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs);
+struct QrLookAhead {        // auxiliary stream, events and second panel workspace for the one-panel look-ahead of geqrf_aug
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    void* work2 = nullptr;  // qr_work_bytes(rows, cols) like `work`
+};
+int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs,
+              const QrLookAhead* la = nullptr);
 int qr_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int rows, int cols, void* work, double* logabs);
 int qr_panel_apply(cudaStream_t st, int mp, int rows, int cols, void* work, cplx* A2, int lda, int n2);
 void qr_work_layout(int rows, int cols, void* work, long long* out6);
 // x <- R^-1 d with R = upper triangle of A[0:n,0:n] and d = column dcol of A (d is overwritten).
 int trsv_upper_aug(cudaStream_t st, cplx* A, int lda, int n, int dcol, cplx* x);
 // Least squares min || A x - b ||: Aaug = [A | b] is rows x (cols+1) and is overwritten; x (cols) <- solution.
-int lstsq_qr_aug(cudaStream_t st, cplx* Aaug, int lda, int rows, int cols, void* work, cplx* x, double* logabs);
+int lstsq_qr_aug(cudaStream_t st, cplx* Aaug, int lda, int rows, int cols, void* work, cplx* x, double* logabs,
+                 const QrLookAhead* la = nullptr);
 
 }  // namespace mspde

@@ -2,6 +2,7 @@
 // Gibbs draw of the last layer (pCN.one_step, /root/reference/mcmc/image_cupy.py:553-617).
 // Everything is enqueued on the context stream; the accept decision is taken on the device, so the host only
 // synchronises when it wants the flags.
+#include <cstdlib>
 #include "context.cuh"
 #include "../../include/mspde.h"
 
@@ -100,7 +101,7 @@ int solve_L_qr(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* x, double*
     if (rc) return rc;
     set_col_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(c->QRaug, c->ldA, N, rhs, N);
     MSPDE_LAUNCH_CHECK();
-    return lstsq_qr_aug(c->stream, c->QRaug, c->ldA, N, N, c->qr_work, x, logabsdet);
+    return lstsq_qr_aug(c->stream, c->QRaug, c->ldA, N, N, c->qr_work, x, logabsdet, &c->qr_la);
 }
 
 int lstsq_general(Ctx* c, const cplx* A, int lda, int rows, int cols, const cplx* b, cplx* x) {
@@ -112,7 +113,7 @@ int lstsq_general(Ctx* c, const cplx* A, int lda, int rows, int cols, const cplx
     if (rc) return rc;
     set_col_kernel<<<(rows + 255) / 256, 256, 0, c->stream>>>(c->QRaug, c->ldA, cols, b, rows);
     MSPDE_LAUNCH_CHECK();
-    return lstsq_qr_aug(c->stream, c->QRaug, c->ldA, rows, cols, c->qr_work, x, nullptr);
+    return lstsq_qr_aug(c->stream, c->QRaug, c->ldA, rows, cols, c->qr_work, x, nullptr, &c->qr_la);
 }
 
 // v = argmin || [H; L] v - rhs ||  (image_cupy.py:596-599)
@@ -124,7 +125,7 @@ int gibbs_lstsq(Ctx* c, const cplx* L, int ldl, const cplx* rhs, cplx* v) {
     if (rc) return rc;
     set_col_kernel<<<(M + N + 255) / 256, 256, 0, c->stream>>>(c->QRaug, c->ldA, N, rhs, M + N);
     MSPDE_LAUNCH_CHECK();
-    return lstsq_qr_aug(c->stream, c->QRaug, c->ldA, M + N, N, c->qr_work, v, nullptr);
+    return lstsq_qr_aug(c->stream, c->QRaug, c->ldA, M + N, N, c->qr_work, v, nullptr, &c->qr_la);
 }
 
 namespace {
@@ -176,6 +177,10 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
         int rc0 = phi_fast_prepare(c, caller);
         if (rc0) return rc0;
     }
+    static const bool dbg = getenv("MSPDE_STEP_TIMING") != nullptr;
+    static cudaEvent_t dt[6];
+    if (dbg && !dt[0]) for (auto& e : dt) cudaEventCreate(&e);
+    if (dbg) cudaEventRecord(dt[0], caller);
     if (!serial) {   // internal streams start after everything already queued on the caller's stream
         MSPDE_CUDA(cudaEventRecord(c->ev_start, caller));
         MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_start, 0));
@@ -201,6 +206,7 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
                     : phi_eval(c, s1, c->pw[1], (const cplx*)ch->L_cur[K - 1], ch->ldl, phi_cur3, serial);
         if (rc) return rc;
         if (!serial && !naive) MSPDE_CUDA(cudaEventRecord(c->ev_s1, s1));
+        if (dbg) cudaEventRecord(dt[1], s1);
     }
     // ---- main stream: layers 0..K-2 (557-564)
     for (int k = 0; k < K - 1; ++k) {
@@ -222,6 +228,7 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
     if (rc) return rc;
     rc = assemble_L(c, c->tp, c->tm, ch->sqrt_betas[K - 1], (cplx*)ch->L_latest[K - 1], ch->ldl);
     if (rc) return rc;
+    if (dbg) cudaEventRecord(dt[2], st);
     // ---- stream s2: Gibbs least squares on [H; L_latest] with both candidate right-hand sides (583-599)
     if (do_gibbs) {
         if (!serial) {
@@ -237,13 +244,14 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
                                                                     ch->beta, ch->betaZ, N, nr, M, c->y, nz->e, cand_acc,
                                                                     cand_rej, c->QRaug, c->ldA);
         MSPDE_LAUNCH_CHECK();
-        rc = geqrf_aug(s2, c->QRaug, c->ldA, M + N, N, 2, c->qr_work, nullptr);
+        rc = geqrf_aug(s2, c->QRaug, c->ldA, M + N, N, 2, c->qr_work, nullptr, &c->qr_la);
         if (rc) return rc;
         rc = trsv_upper_aug(s2, c->QRaug, c->ldA, N, N, v_acc);
         if (rc) return rc;
         rc = trsv_upper_aug(s2, c->QRaug, c->ldA, N, N + 1, v_rej);
         if (rc) return rc;
         if (!serial) MSPDE_CUDA(cudaEventRecord(c->ev_s2, s2));
+        if (dbg) cudaEventRecord(dt[3], s2);
     } else {
         gibbs_candidates_kernel<<<(M + N + 255) / 256, 256, 0, st>>>((const cplx*)ch->noise_cur[K - 1],
                                                                     (const cplx*)ch->noise_new[K - 1], (const cplx*)nz->w_last,
@@ -256,12 +264,21 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
          : fast ? phi_eval_fast(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3)
                 : phi_eval(c, st, c->pw[0], (const cplx*)ch->L_latest[K - 1], ch->ldl, phi_new3, serial);
     if (rc) return rc;
+    if (dbg) cudaEventRecord(dt[4], st);
     if (!serial) {
         if (!cached && !naive) MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_s1, 0));
         if (do_gibbs) MSPDE_CUDA(cudaStreamWaitEvent(st, c->ev_s2, 0));
     }
     accept_kernel<<<1, 32, 0, st>>>(phi_cur3, phi_new3, nz->log_u, out_dev);                              // 573
     MSPDE_LAUNCH_CHECK();
+    if (dbg) {
+        cudaEventRecord(dt[5], st);
+        cudaDeviceSynchronize();
+        float a, b, d, e, f;
+        cudaEventElapsedTime(&a, dt[0], dt[1]); cudaEventElapsedTime(&b, dt[0], dt[2]); cudaEventElapsedTime(&d, dt[0], dt[3]);
+        cudaEventElapsedTime(&e, dt[0], dt[4]); cudaEventElapsedTime(&f, dt[0], dt[5]);
+        fprintf(stderr, "[step] phi_cur done %.1f | L_latest ready %.1f | gibbs done %.1f | phi_new done %.1f | joined %.1f ms\n", a, b, d, e, f);
+    }
     for (int k = 0; k < K; ++k) {                                                                        // 575-579
         cond_copy_kernel<<<nb, 256, 0, st>>>(out_dev, (const double2*)ch->u_new[k], (double2*)ch->u_cur[k], N);
         cond_copy_kernel<<<nb, 256, 0, st>>>(out_dev, (const double2*)ch->noise_new[k], (double2*)ch->noise_cur[k], N);

@@ -322,13 +322,25 @@ __global__ void __launch_bounds__(T::NTHREADS, T::BN == 32 ? 2 : 1) zgemm3m_tn_k
     const bool conj = p.conjA != 0;
     const double csign = conj ? -1.0 : 1.0;      // A enters T3 as Ar + csign * Ai
 
+    // beta != 0: the C tile is read up front into the accumulators (T1 <- s*cr, T3 <- s*(cr + ci), s = beta/alpha, which the
+    // epilogue's T1 -+ T2 and T3 - T1 -+ T2 turn back into s*c + product), so its latency overlaps the first bulk copies
+    const bool preload = p.beta != 0.0 && p.alpha != 0.0;
+    const double cscale = preload ? p.beta / p.alpha : 0.0;
     double t1[2][2][2], t2[2][2][2], t3[2][2][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
-            for (int c = 0; c < 2; ++c) t1[a][b][c] = t2[a][b][c] = t3[a][b][c] = 0.0;
+            for (int c = 0; c < 2; ++c) {
+                t1[a][b][c] = t2[a][b][c] = t3[a][b][c] = 0.0;
+                const int i = i0 + wi * 16 + a * 8 + g, j = j0 + wj * 16 + b * 8 + 2 * t + c;
+                if (preload && i < p.m && j < p.n) {
+                    const cplx cv = C[size_t(i) * p.ldc + j];
+                    t1[a][b][c] = cscale * cv.x;
+                    t3[a][b][c] = cscale * (cv.x + cv.y);
+                }
+            }
 
     int stage = 0;
     uint32_t parity = 0;
@@ -412,7 +424,7 @@ __global__ void __launch_bounds__(T::NTHREADS, T::BN == 32 ? 2 : 1) zgemm3m_tn_k
                 const double re = conj ? x1 + x2 : x1 - x2;
                 const double im = conj ? (x3 - x1) + x2 : (x3 - x1) - x2;
                 cplx out = make_double2(alpha * re, alpha * im);
-                if (beta != 0.0) {
+                if (beta != 0.0 && !preload) {
                     cplx cv = crow[j];
                     out.x = fma(beta, cv.x, out.x);
                     out.y = fma(beta, cv.y, out.y);
