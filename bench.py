@@ -137,7 +137,7 @@ def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
     rate, desc, cores, dt = cpu_oracle_rate(cfg, steps=max(1, args.steps), warmup=min(args.warmup, 1), budget_s=30.0)
-    line = {"impl": "reference", "metric": "pCN iters/sec (n=32, 3 layers)", "value": rate, "unit": "iters/s",
+    line = {"impl": "reference", "metric": f"pCN iters/sec (n={cfg['n']}, {cfg['n_layers']} layers)", "value": rate, "unit": "iters/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / rate,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(cfg, args.gpus),
@@ -147,10 +147,13 @@ def run_reference(args, cfg, rank, world):
 
 
 def workload_config(cfg, gpus):
-    return {"workload": f"BASELINE configs[1]: Shepp-Logan tomography, {cfg['n_layers']} layers, n={cfg['n']} modes/axis, "
+    idx = {16: 0, 32: 1, 64: 2, 96: 4}.get(cfg["n"], 1)       # position in BASELINE.json "configs"
+    N, M = (2 * cfg["n"] - 1) ** 2, (2 * cfg["n_ext"] - 1) * cfg["n_theta"]
+    return {"workload": f"BASELINE configs[{idx}]: Shepp-Logan tomography, {cfg['n_layers']} layers, n={cfg['n']} modes/axis, "
                         f"n_ext={cfg['n_ext']}, {cfg['n_theta']} angles, one chain per GPU",
             "formulation": "reference-faithful (Phi(current) recomputed every step, Gibbs QR every step)",
-            "cache": "working set per step (L 252 MB, Q_inv 2.1 GB, H 726 MB) >> 126 MB L2; no explicit flush",
+            "cache": f"working set per step (L {16e-6 * N * N:.0f} MB, Q_inv {16e-9 * M * M:.1f} GB, H {16e-6 * N * M:.0f} MB) >> 126 MB L2; "
+                     "no explicit flush",
             "parallelism": f"{gpus} independent chain(s), no data-path collective; final NCCL all_gather of samples"}
 
 
@@ -475,7 +478,7 @@ def main():
         cpu_baseline = {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": desc}
 
     if rank == 0:
-        line = {"metric": "pCN iters/sec (n=32, 3 layers)", "value": value, "unit": "iters/s", "n_gpus": world,
+        line = {"metric": f"pCN iters/sec (n={cfg['n']}, {cfg['n_layers']} layers)", "value": value, "unit": "iters/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(cfg, world),
