@@ -62,3 +62,18 @@ def test_ctx_create_rejects_bad_arguments_without_touching_the_gpu():
     h = ctypes.c_void_p()
     rc = _ffi.lib().mspde_ctx_create(ctypes.byref(h), 0, 1, 1, 10, 3, None)    # n < 2
     assert rc < 0 and b"bad arguments" in _ffi.lib().mspde_last_error()
+
+
+def test_gemm_mode_switch_is_host_only():
+    """mspde_set_gemm_mode / mspde_get_gemm_mode (include/mspde.h): 3M is the default, 4M selectable, anything else rejected."""
+    default = _ffi.get_gemm_mode()
+    if not os.environ.get("MSPDE_GEMM"):
+        assert default == _ffi.GEMM_3M
+    try:
+        _ffi.set_gemm_mode(_ffi.GEMM_4M)
+        assert _ffi.get_gemm_mode() == _ffi.GEMM_4M
+        with pytest.raises(_ffi.MspdeError):
+            _ffi.set_gemm_mode(7)
+        assert _ffi.get_gemm_mode() == _ffi.GEMM_4M
+    finally:
+        _ffi.set_gemm_mode(default)
