@@ -93,10 +93,13 @@ def cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=30.0):
     Returns (iters_per_s_at_cfg, description, cores)."""
     from oracle import mspde_oracle as o
     try:
-        from threadpoolctl import threadpool_info
+        # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core it may run on
+        from threadpoolctl import threadpool_info, threadpool_limits
+        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        threadpool_limits(limits=avail)
         cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
-        cores = os.cpu_count() or 1
+        cores = int(os.environ.get("OMP_NUM_THREADS", 0)) or os.cpu_count() or 1
     a = (np.random.rand(2000, 2000) + 1j * np.random.rand(2000, 2000))
     a @ a
     t0 = time.perf_counter(); a @ a; t1 = time.perf_counter()
