@@ -237,23 +237,28 @@ __global__ void __launch_bounds__(THREADS, 2) zgemm_tn_kernel(GemmArgs p) {
 // One DMMA.8x8x4 is a real 8 x 8 x 4 product here: a lane loads one complex A element (k = t, row g) and one complex B
 // element (k = t, col g) with a 128-bit shared-memory load and feeds re, im and re+-im to the three accumulator sets.
 // Three accumulator sets cost 1.5x the registers, so the CTA tile is 64 x 32 (8 MMA warps of 16 x 16), still 2 CTAs/SM.
-template <int BN_, int STAGES_>
+template <int BN_, int STAGES_, int MF_>
 struct M3 {
     static constexpr int BM = 64, BN = BN_, BK = 16, STAGES = STAGES_;
     static constexpr int PA = BM + 2;   // pitch == 2 mod 8 (complex): the 8 lanes of a 128-bit quarter-warp load hit 8 distinct 16 B slots
     static constexpr int PB = BN + 2;
-    static constexpr int WARPS = 4 * (BN / 16);          // MMA warps: 4 along i x BN/16 along j, 16 x 16 each
+    static constexpr int MF = MF_;                       // 8-row A fragments per warp: warp tile (8 MF) x 16
+    static constexpr int WI = BM / (8 * MF);             // MMA warps along i
+    static constexpr int WARPS = WI * (BN / 16);
     static constexpr int NTHREADS = (WARPS + 1) * 32;
     static constexpr int STAGE_DOUBLES = (BK * PA + BK * PB) * 2;
     static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
 };
-typedef M3<32, 4> M3N;    // 64 x 32 tile, 288 threads, 2 CTAs/SM.  (A 64 x 64 tile with 16 MMA warps at 1 CTA/SM measured 2-25 % slower.)
+typedef M3<32, 4, 2> M3N;    // 8 MMA warps of 16 x 16: the general kernel
+typedef M3<32, 4, 4> M3T;    // 4 MMA warps of 32 x 16 (168 registers): 6 instead of 8 operand sums per 24 DMMAs, +3 % when k is long enough to
+                             // amortise the thinner latency cover of 8 MMA warps per SM (k >= 1024); 10-20 % slower on k <= 128 updates    // 64 x 32 tile, 288 threads, 2 CTAs/SM.  (A 64 x 64 tile with 16 MMA warps at 1 CTA/SM measured 2-25 % slower.)
 
 template <class T>
-__global__ void __launch_bounds__(T::NTHREADS, T::BN == 32 ? 2 : 1) zgemm3m_tn_kernel(GemmArgs p) {
+__global__ void __launch_bounds__(T::NTHREADS, 2) zgemm3m_tn_kernel(GemmArgs p) {
     constexpr int BM = T::BM, BN = T::BN, BK = T::BK, STAGES = T::STAGES, PA = T::PA, PB = T::PB;
     constexpr int STAGE_DOUBLES = T::STAGE_DOUBLES;
     constexpr int CONSUMER_WARPS = T::WARPS;
+    constexpr int MF = T::MF, WI = T::WI;
     const int tiles_i = (p.m + BM - 1) / BM, tiles_j = (p.n + BN - 1) / BN;
     const int pid = blockIdx.x;
     const int per_group = GROUP_I * tiles_j;
@@ -315,9 +320,9 @@ __global__ void __launch_bounds__(T::NTHREADS, T::BN == 32 ? 2 : 1) zgemm3m_tn_k
 
     const int g = lane >> 2;
     const int t = lane & 3;
-    const int wi = warp & 3;          // 4 warps along i (16 rows each)
-    const int wj = warp >> 2;         // 2 warps along j (16 complex cols each)
-    const int a_off = (t * PA + wi * 16 + g) * 2;                 // doubles; + kk*4*PA*2 per k4 step, + 16 per fragment
+    const int wi = warp % WI;         // WI warps along i (8 MF rows each)
+    const int wj = warp / WI;         // BN/16 warps along j (16 complex cols each)
+    const int a_off = (t * PA + wi * 8 * MF + g) * 2;                 // doubles; + kk*4*PA*2 per k4 step, + 16 per fragment
     const int b_off = (BK * PA + t * PB + wj * 16 + g) * 2;
     const bool conj = p.conjA != 0;
     const double csign = conj ? -1.0 : 1.0;      // A enters T3 as Ar + csign * Ai
@@ -326,15 +331,15 @@ __global__ void __launch_bounds__(T::NTHREADS, T::BN == 32 ? 2 : 1) zgemm3m_tn_k
     // epilogue's T1 -+ T2 and T3 - T1 -+ T2 turn back into s*c + product), so its latency overlaps the first bulk copies
     const bool preload = p.beta != 0.0 && p.alpha != 0.0;
     const double cscale = preload ? p.beta / p.alpha : 0.0;
-    double t1[2][2][2], t2[2][2][2], t3[2][2][2];
+    double t1[MF][2][2], t2[MF][2][2], t3[MF][2][2];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < MF; ++a)
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 t1[a][b][c] = t2[a][b][c] = t3[a][b][c] = 0.0;
-                const int i = i0 + wi * 16 + a * 8 + g, j = j0 + wj * 16 + b * 8 + 2 * t + c;
+                const int i = i0 + wi * 8 * MF + a * 8 + g, j = j0 + wj * 16 + b * 8 + 2 * t + c;
                 if (preload && i < p.m && j < p.n) {
                     const cplx cv = C[size_t(i) * p.ldc + j];
                     t1[a][b][c] = cscale * cv.x;
@@ -351,26 +356,26 @@ __global__ void __launch_bounds__(T::NTHREADS, T::BN == 32 ? 2 : 1) zgemm3m_tn_k
         if (kvalid >= BK) {
 #pragma unroll
             for (int kk = 0; kk < BK / 4; ++kk) {
-                double2 av[2], bv[2];
-                double as[2], bs[2];
+                double2 av[MF], bv[2];
+                double as[MF], bs[2];
 #pragma unroll
-                for (int a = 0; a < 2; ++a) av[a] = *reinterpret_cast<const double2*>(S + a_off + kk * 4 * PA * 2 + a * 16);
+                for (int a = 0; a < MF; ++a) av[a] = *reinterpret_cast<const double2*>(S + a_off + kk * 4 * PA * 2 + a * 16);
 #pragma unroll
                 for (int b = 0; b < 2; ++b) bv[b] = *reinterpret_cast<const double2*>(S + b_off + kk * 4 * PB * 2 + b * 16);
-                as[0] = fma(csign, av[0].y, av[0].x);
-                as[1] = fma(csign, av[1].y, av[1].x);
+#pragma unroll
+                for (int a = 0; a < MF; ++a) as[a] = fma(csign, av[a].y, av[a].x);
                 bs[0] = bv[0].x + bv[0].y;
                 bs[1] = bv[1].x + bv[1].y;
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
+                for (int a = 0; a < MF; ++a)
 #pragma unroll
                     for (int b = 0; b < 2; ++b) dmma884(t1[a][b][0], t1[a][b][1], av[a].x, bv[b].x);
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
+                for (int a = 0; a < MF; ++a)
 #pragma unroll
                     for (int b = 0; b < 2; ++b) dmma884(t2[a][b][0], t2[a][b][1], av[a].y, bv[b].y);
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
+                for (int a = 0; a < MF; ++a)
 #pragma unroll
                     for (int b = 0; b < 2; ++b) dmma884(t3[a][b][0], t3[a][b][1], as[a], bs[b]);
             }
@@ -379,10 +384,10 @@ __global__ void __launch_bounds__(T::NTHREADS, T::BN == 32 ? 2 : 1) zgemm3m_tn_k
             const int nk4 = (kvalid + 3) >> 2;
             for (int kk = 0; kk < nk4; ++kk) {
                 const bool dead = (kk * 4 + t) >= kvalid;
-                double2 av[2], bv[2];
-                double as[2], bs[2];
+                double2 av[MF], bv[2];
+                double as[MF], bs[2];
 #pragma unroll
-                for (int a = 0; a < 2; ++a) {
+                for (int a = 0; a < MF; ++a) {
                     av[a] = dead ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(S + a_off + kk * 4 * PA * 2 + a * 16);
                     as[a] = fma(csign, av[a].y, av[a].x);
                 }
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(T::NTHREADS, T::BN == 32 ? 2 : 1) zgemm3m_tn_k
                     bs[b] = bv[b].x + bv[b].y;
                 }
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
+                for (int a = 0; a < MF; ++a)
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
                         dmma884(t1[a][b][0], t1[a][b][1], av[a].x, bv[b].x);
@@ -409,8 +414,8 @@ __global__ void __launch_bounds__(T::NTHREADS, T::BN == 32 ? 2 : 1) zgemm3m_tn_k
     // epilogue: the accumulator fragment (row g, cols 2t, 2t+1) is two adjacent complex C elements
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const int i = i0 + wi * 16 + a * 8 + g;
+    for (int a = 0; a < MF; ++a) {
+        const int i = i0 + wi * 8 * MF + a * 8 + g;
         if (i >= p.m) continue;
         cplx* crow = C + size_t(i) * p.ldc;
 #pragma unroll
@@ -477,13 +482,18 @@ int launch(cudaStream_t st, const GemmArgs& a, int nz) {
     if (!g_attr_set) {
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm3m_tn_kernel<M3N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3N::SMEM_BYTES));
+        MSPDE_CUDA(cudaFuncSetAttribute(zgemm3m_tn_kernel<M3T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3T::SMEM_BYTES));
         g_attr_set = true;
     }
     static FILE* logf = getenv("MSPDE_GEMM_LOG") ? fopen(getenv("MSPDE_GEMM_LOG"), "w") : nullptr;   // dev aid: shapes per launch
     if (logf) { fprintf(logf, "%d %d %d %d %d\n", a.m, a.n, a.k, a.uplo, nz); fflush(logf); }
     if (use3m) {
         dim3 grid(((a.m + M3N::BM - 1) / M3N::BM) * ((a.n + M3N::BN - 1) / M3N::BN), 1, nz);
-        zgemm3m_tn_kernel<M3N><<<grid, M3N::NTHREADS, M3N::SMEM_BYTES, st>>>(a);
+        static const int long_k = getenv("MSPDE_GEMM_LONG_K") ? atoi(getenv("MSPDE_GEMM_LONG_K")) : 1024;   // dev hook
+        if (min(a.k, a.kslice) >= long_k)
+            zgemm3m_tn_kernel<M3T><<<grid, M3T::NTHREADS, M3T::SMEM_BYTES, st>>>(a);
+        else
+            zgemm3m_tn_kernel<M3N><<<grid, M3N::NTHREADS, M3N::SMEM_BYTES, st>>>(a);
     } else {
         dim3 grid(((a.m + BM - 1) / BM) * ((a.n + BN - 1) / BN), 1, nz);
         zgemm_tn_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(a);
