@@ -85,6 +85,28 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+_RESULT_FD = None
+
+
+def reserve_stdout():
+    """stdout carries exactly one JSON line: keep the real stdout aside and send everything else that libraries write to
+    file descriptor 1 (NCCL's version banner, for one) to stderr."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    text = json.dumps(line) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text.encode())
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arm: the numpy oracle (port of the reference step) on the host cores, on a bounded sample
 # ----------------------------------------------------------------------------------------------------------------
@@ -146,7 +168,7 @@ def run_reference(args, cfg, rank, world):
             "config": workload_config(cfg, args.gpus),
             "cpu_baseline": {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": rate, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(cfg, gpus):
@@ -176,6 +198,7 @@ def main():
     ap.add_argument("--chains-per-gpu", type=int, default=1,
                     help="config 4 (many independent chains): also report the throughput with this many chains in flight per GPU")
     args = ap.parse_args()
+    reserve_stdout()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,7 +236,7 @@ def main():
         checks = stp.run_overlapped()["checks"]
         sec = sum(r["seconds"] for r in runs) / len(runs)
         if rank == 0:
-            print(json.dumps({"metric": "pCN iters/sec (n=96, 3 layers, one chain block-distributed)", "value": 1.0 / sec,
+            emit({"metric": "pCN iters/sec (n=96, 3 layers, one chain block-distributed)", "value": 1.0 / sec,
                               "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1),
                               "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                               "dtype": "f64", "data": "synthetic",
@@ -224,7 +247,7 @@ def main():
                                            "aggregate_tflops": f_iter / sec / 1e12, "traffic": None},
                               "gemm_scheme": "3m" if _ffi.get_gemm_mode() == _ffi.GEMM_3M else "4m",
                               "clocks": clocks, "finite": all(r["finite"] for r in runs), "residual_checks": checks,
-                              "phi_latest": runs[-1]["phi"]}))
+                              "phi_latest": runs[-1]["phi"]})
         dist.destroy_process_group()
         return
     K = cfg["n_layers"]
@@ -490,7 +513,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "gemm_scheme": "3m" if gemm_mode == _ffi.GEMM_3M else "4m", "acceptance_rate": acc_rate, "setup_s": t_setup}
         line.update(extra)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
