@@ -453,10 +453,10 @@ def main():
                     "flops_per_launch": fl, "zgemm_equivalent": {"flops_per_launch": fl8, "achieved": fl8 / (ms_k * 1e-3) / 1e12,
                                                                  "note": "same launch counted at 8 flop per complex multiply-add, "
                                                                          "the convention ZGEMM rates are quoted in"},
-                    "traffic": 17.0e9 if gemm_mode == _ffi.GEMM_3M else 13.1e9,
+                    "traffic": 15.5e9 if gemm_mode == _ffi.GEMM_3M else 13.1e9,
                     "traffic_source": "dram__bytes_read+write of this launch from one ncu --set full capture: "
-                                      + ("profiles/r01_zgemm3m_full.ncu-rep (15.93e9 read + 1.05e9 written; algorithmic 0.73e9 + 1.05e9: "
-                                         "operand panels are re-read from DRAM when a wave's working set leaves the L2, 84 % L2 hit rate)"
+                                      + ("profiles/r01_zgemm3m_k1024_full.ncu-rep (14.47e9 read + 1.04e9 written; algorithmic 0.73e9 + 1.05e9: "
+                                         "operand panels are re-read from DRAM when a wave's working set leaves the L2, 86 % L2 hit rate)"
                                          if gemm_mode == _ffi.GEMM_3M else
                                          "profiles/r01_zgemm_full_v2.ncu-rep (grouped tile rasterisation; 56.2e9 before it)"),
                     "ms_per_launch": ms_k,
