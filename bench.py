@@ -451,8 +451,10 @@ def main():
         roofline = {"kernel": "zgemm_tn_kernel (DMMA m8n8k4, %s), launch Q_inv = I - Ht^H Ht, upper triangle, m=n=%d k=%d" % (scheme, M, N),
                     "bound": "tensor", "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
                     "flops_per_launch": fl, "zgemm_equivalent": {"flops_per_launch": fl8, "achieved": fl8 / (ms_k * 1e-3) / 1e12,
-                                                                 "note": "same launch counted at 8 flop per complex multiply-add, "
-                                                                         "the convention ZGEMM rates are quoted in"},
+                                                                 "frac": fl8 / (ms_k * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                                                                 "note": "same launch counted at 8 flop per complex multiply-add (SURVEY 8d's "
+                                                                         "ZHERK = 4 n^2 k), the convention ZGEMM rates are quoted in; above 1.0 "
+                                                                         "under 3M because the kernel's algorithm needs 6"},
                     "traffic": 15.5e9 if gemm_mode == _ffi.GEMM_3M else 13.1e9,
                     "traffic_source": "dram__bytes_read+write of this launch from one ncu --set full capture: "
                                       + ("profiles/r01_zgemm3m_k1024_full.ncu-rep (14.47e9 read + 1.04e9 written; algorithmic 0.73e9 + 1.05e9: "
