@@ -448,7 +448,8 @@ def main():
         ach = fl / (ms_k * 1e-3) / 1e12
         step_rate = f_iter / (ms_dev * 1e-3 / args.steps) / 1e12
         scheme = "3M: three real DMMA products per complex product" if gemm_mode == _ffi.GEMM_3M else "4M: four real DMMA products"
-        roofline = {"kernel": "zgemm_tn_kernel (DMMA m8n8k4, %s), launch Q_inv = I - Ht^H Ht, upper triangle, m=n=%d k=%d" % (scheme, M, N),
+        kname = "zgemm3m_tn_kernel" if gemm_mode == _ffi.GEMM_3M else "zgemm_tn_kernel"
+        roofline = {"kernel": "%s (DMMA m8n8k4, %s), launch Q_inv = I - Ht^H Ht, upper triangle, m=n=%d k=%d" % (kname, scheme, M, N),
                     "bound": "tensor", "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
                     "flops_per_launch": fl, "zgemm_equivalent": {"flops_per_launch": fl8, "achieved": fl8 / (ms_k * 1e-3) / 1e12,
                                                                  "frac": fl8 / (ms_k * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
