@@ -36,7 +36,9 @@ CONFIGS = {
     3: dict(n=64, n_ext=64, n_theta=90, n_layers=3),
     5: dict(n=96, n_ext=96, n_theta=90, n_layers=3),   # one chain, every dense piece block-distributed (needs >= 2 GPUs)
 }
-FP64_PEAK_TFLOPS = 37.15   # measured on this pool's B200: DMMA m8n8k4 microbenchmark, profiles/r01_fp64_probe.log
+FP64_PEAK_FALLBACK = 37.15  # DMMA m8n8k4 microbenchmark of round 1 (profiles/r01_fp64_probe.log); bench.py re-measures it live
+REFERENCE_BUDGET_S = 200.0  # wall budget of the timed region of --impl reference
+BENCH_BETA = 0.04           # pCN step of the bench chains: 15-35 % acceptance over the timed region
 
 
 def flops_iter(n, n_ext, n_theta, n_layers):
@@ -111,8 +113,9 @@ def emit(line):
 # CPU arm: the numpy oracle (port of the reference step) on the host cores, on a bounded sample
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=30.0):
-    """Times the oracle's one_step on the largest geometry that fits the budget and scales to `cfg` by flop ratio.
-    Returns (iters_per_s_at_cfg, description, cores)."""
+    """Times the oracle's one_step AT THE LABELLED CONFIG (same n, angles, layers; never a smaller geometry scaled up).
+    Runs at most `steps` iterations and stops early once `budget_s` of wall time is used (at least one iteration always
+    completes), so a K-step request stays bounded.  Returns (iters_per_s, description, cores, seconds_per_iter, steps_timed)."""
     from oracle import mspde_oracle as o
     try:
         # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core it may run on
@@ -122,23 +125,9 @@ def cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=30.0):
         cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
         cores = int(os.environ.get("OMP_NUM_THREADS", 0)) or os.cpu_count() or 1
-    a = (np.random.rand(2000, 2000) + 1j * np.random.rand(2000, 2000))
-    a @ a
-    t0 = time.perf_counter(); a @ a; t1 = time.perf_counter()
-    gfs = 8 * 2000 ** 3 / (t1 - t0)
-    per_step = min(budget_s, 240.0 / max(1, steps + warmup))
-    f_target, _, _ = flops_iter(**cfg)
-    cands = [(cfg["n"], cfg["n_theta"]), (24, 60), (16, 45), (12, 30), (8, 24)]
-    chosen = cands[-1]
-    for n, nth in cands:
-        if n > cfg["n"]:
-            continue
-        f, _, _ = flops_iter(n, cfg["n_ext"], nth, cfg["n_layers"])
-        if 2.5 * f / gfs <= per_step:   # numpy (full GEMMs, explicit Q, LU of a triangle) does ~2.5x the structured count
-            chosen = (n, nth)
-            break
-    n, nth = chosen
-    hp = o.Hyper(n_layers=cfg["n_layers"], n=n, n_ext=cfg["n_ext"], n_theta=nth)
+    a = (np.random.rand(1500, 1500) + 1j * np.random.rand(1500, 1500))
+    a @ a                                                   # BLAS thread pool warm-up
+    hp = o.Hyper(n_layers=cfg["n_layers"], n=cfg["n"], n_ext=cfg["n_ext"], n_theta=cfg["n_theta"], beta=BENCH_BETA)
     pb = o.synthetic_problem(hp)
     ft, H, HtH, y, delta = pb["ft"], pb["H"], pb["HtH"], pb["y"], pb["delta"]
     ns = o.NoiseStream(11, hp.n_layers, ft.n_ravel, H.shape[0])
@@ -146,29 +135,118 @@ def cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=30.0):
     st = o.init_chain(hp, ft, [ns.half() for _ in range(K)], [ns.half() for _ in range(K)])
     for _ in range(warmup):
         o.one_step(st, ft, H, HtH, y, delta, ns.draw_iteration())
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    done, t0 = 0, time.perf_counter()
+    while done < max(1, steps):
         o.one_step(st, ft, H, HtH, y, delta, ns.draw_iteration())
-    dt = (time.perf_counter() - t0) / steps
-    f_sample, _, _ = flops_iter(n, cfg["n_ext"], nth, cfg["n_layers"])
-    rate = (1.0 / dt) * (f_sample / f_target)
-    desc = (f"{steps} full oracle iteration(s) at n={n}, {nth} angles, {cfg['n_layers']} layers ({dt:.2f} s each, numpy/OpenBLAS "
-            f"{cores} threads)" + ("" if (n, nth) == (cfg["n"], cfg["n_theta"]) else
-                                   f", scaled to the workload by the F_iter ratio {f_sample / f_target:.4f}"))
-    return rate, desc, cores, dt
+        done += 1
+        if time.perf_counter() - t0 >= budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
+    desc = (f"{done} full oracle iteration(s) of the labelled workload itself (n={cfg['n']}, {cfg['n_theta']} angles, "
+            f"{cfg['n_layers']} layers; {dt:.2f} s each, numpy/OpenBLAS on {cores} threads); no scaling or extrapolation")
+    return 1.0 / dt, desc, cores, dt, done
 
 
 def run_reference(args, cfg, rank, world):
+    """--impl reference: the CPU port of the reference step on all host cores, at the labelled config.  One n=32 iteration is
+    25-40 s of CPU, so the timed run is bounded by wall time (REFERENCE_BUDGET_S) and reports how many steps it timed."""
     if rank != 0:
         return
-    rate, desc, cores, dt = cpu_oracle_rate(cfg, steps=max(1, args.steps), warmup=min(args.warmup, 1), budget_s=30.0)
+    rate, desc, cores, dt, done = cpu_oracle_rate(cfg, steps=max(1, args.steps), warmup=0, budget_s=REFERENCE_BUDGET_S)
     line = {"impl": "reference", "metric": f"pCN iters/sec (n={cfg['n']}, {cfg['n_layers']} layers)", "value": rate, "unit": "iters/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / rate,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(cfg, args.gpus),
+            "n_gpus": args.gpus, "steps": done, "warmup": 0, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(cfg, args.gpus),
             "cpu_baseline": {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": desc},
-            "e2e": {"value": rate, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": rate, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": f"timed {done} of the requested {args.steps} steps (wall budget {REFERENCE_BUDGET_S:.0f} s; BLAS needs no warm-up "
+                    "steps); value = steps / their wall time, ms_per_step x steps = the timed wall time"}
     emit(line)
+
+
+def library_standin_ms(sim, noise, reps=2):
+    """The same pCN iteration written with library calls only -- torch.fft (cuFFT), `@` (cuBLAS ZGEMM), torch.linalg cholesky /
+    solve / solve_triangular / lstsq (cuSOLVER) -- i.e. what the reference's CuPy path does on this box (BASELINE.md 4.4,
+    SURVEY 8d: "the reference's library-call GPU path on the same box our kernels must beat").  Structure-exploiting where the
+    libraries allow it (triangular solve instead of the reference's LU of a triangle, lstsq instead of an explicit Q), same
+    inputs, same process.  Returns ms per step (CUDA events, best of `reps` after one warm-up)."""
+    import torch
+    from mspde import util
+    pcn, ctx, Layers, f = sim.pcn, sim.pcn.ctx, sim.Layers, sim.fourier
+    N, M = ctx.N, ctx.M
+    n, il = f.basis_number, 2 * f.basis_number - 1
+    dev = ctx.device
+    wh, log_u, wl, e = noise
+    idx = torch.arange(il * il, device=dev)
+    blk, inn = idx // il, idx % il
+    dij, dkl = blk[:, None] - blk[None, :], inn[:, None] - inn[None, :]
+    mask = (dij.abs() <= n - 1) & (dkl.abs() <= n - 1)
+    r_i, c_i = (dkl + n - 1).clamp(0, il - 1), (dij + n - 1).clamp(0, il - 1)
+    del dij, dkl
+    zero = torch.zeros((), dtype=torch.complex128, device=dev)
+    I_N = torch.eye(N, dtype=torch.complex128, device=dev)
+    I_M = torch.eye(M, dtype=torch.complex128, device=dev)
+    Hc, Hct, yc = ctx.H.contiguous(), ctx.Hct.contiguous(), ctx.y.to(torch.complex128)
+
+    def assemble(u_sym, sb):
+        uh = util.from_u_2D_ravel_to_uHalf_2D(u_sym, n)
+        img = f.irfft2(uh)
+        tp = util.symmetrize_2D(f.rfft2(torch.exp(img)))
+        tm = util.symmetrize_2D(f.rfft2(torch.exp(-img)))
+        return (torch.where(mask, tp[r_i, c_i], zero) * ctx.D_diag - torch.where(mask, tm[r_i, c_i], zero)) / sb
+
+    def phi(L):
+        r = L.conj().T @ L + ctx.HtH + ctx.delta * I_N
+        c = torch.linalg.cholesky(r)
+        Ht = torch.linalg.solve_triangular(c, Hct, upper=False)
+        C = torch.linalg.cholesky(I_M - Ht.conj().T @ Ht)
+        return 0.5 * torch.linalg.norm(yc @ C) ** 2 - torch.log(torch.diagonal(C).real).sum()
+
+    def step():
+        K = len(Layers)
+        u_prev = None
+        for k in range(K - 1):
+            nn = pcn.betaZ * Layers[k]._noise_cur + pcn.beta * util.symmetrize(wh[k])
+            if k == 0:
+                u_prev = ctx.stdev_sym * nn
+            else:
+                Lk = assemble(u_prev, Layers[k].LMat.sqrt_beta)
+                u_prev = torch.linalg.solve(Lk, nn)
+                del Lk
+        phi_cur = phi(Layers[-1].LMat.current_L.contiguous())
+        L2 = assemble(u_prev, Layers[-1].LMat.sqrt_beta)
+        phi_new = phi(L2)
+        acc = bool((phi_cur - phi_new) > log_u)                              # the reference's host sync (573)
+        nn = pcn.betaZ * (Layers[-1]._noise_new if acc else Layers[-1]._noise_cur) + pcn.beta * util.symmetrize(wl)
+        rhs = torch.cat(((ctx.y - e).to(torch.complex128), -nn))
+        A = torch.cat((Hc, L2), 0)
+        return torch.linalg.lstsq(A, rhs.unsqueeze(1)).solution
+
+    step()
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def measure_fp64_peak(_ffi):
+    """FP64 DMMA peak of THIS box, measured now by mspde_fp64_peak_probe (MEASURED_PEAKS.json has no FP64 entry)."""
+    import ctypes
+    v = ctypes.c_double(0.0)
+    try:
+        _ffi.check(_ffi.lib().mspde_fp64_peak_probe(_ffi.current_stream(), ctypes.byref(v)), "fp64_peak_probe")
+        if 10.0 < v.value < 100.0:
+            return float(v.value), ("measured live on this GPU by mspde_fp64_peak_probe (register-resident DMMA m8n8k4 chain, 16 "
+                                    "warps/SM, best of 3); MEASURED_PEAKS.json has no FP64 entry")
+    except Exception as ex:                                   # never lose the bench line to the probe
+        sys.stderr.write(f"fp64 probe failed: {ex}\n")
+    return FP64_PEAK_FALLBACK, "round-1 probe value (profiles/r01_fp64_probe.log); live probe unavailable"
 
 
 def workload_config(cfg, gpus):
@@ -195,9 +273,13 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the separately-reported results-preserving formulations")
     ap.add_argument("--gemm", default=None, choices=["3m", "4m"],
                     help="complex product scheme of the GEMM kernel for the headline (default: the library's, 3m)")
+    ap.add_argument("--beta", type=float, default=None, help="pCN step size of the bench chains (default BENCH_BETA)")
     ap.add_argument("--chains-per-gpu", type=int, default=1,
                     help="config 4 (many independent chains): also report the throughput with this many chains in flight per GPU")
     args = ap.parse_args()
+    if args.beta is not None:
+        global BENCH_BETA
+        BENCH_BETA = args.beta
     reserve_stdout()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -218,6 +300,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     f_iter, N, M = flops_iter(**cfg)
+    FP64_PEAK_TFLOPS, fp64_peak_source = measure_fp64_peak(_ffi)
     if args.config == 5:
         # BASELINE configs[4]: a single n=96 chain whose dense work is block-distributed over the GPUs (strong scaling)
         from mspde.dist import DistStep
@@ -252,7 +335,7 @@ def main():
         return
     K = cfg["n_layers"]
     t_setup = time.perf_counter()
-    sim = im.Simulation(n_layers=K, n_samples=args.steps * 2 + args.warmup * 2 + 8, n=cfg["n"], n_extended=cfg["n_ext"], beta=0.3,
+    sim = im.Simulation(n_layers=K, n_samples=args.steps * 2 + args.warmup * 2 + 8, n=cfg["n"], n_extended=cfg["n_ext"], beta=BENCH_BETA,
                         kappa=5e9, sigma_0=4e7, sigma_v=3.2e4, sigma_scaling=0.4, meas_std=0.2, evaluation_interval=10,
                         printProgress=False, seed=1 + rank, burn_percentage=25.0, enable_step_adaptation=True,
                         pcn_variant="dunlop", phantom_name="shepp.png", meas_type="tomo", n_theta=cfg["n_theta"],
@@ -395,7 +478,7 @@ def main():
         # BASELINE configs[3]: independent chains sharded over the GPUs.  Several chains per GPU are kept in flight on their
         # own streams (each with its own context), which fills the latency-bound gaps of one chain with the GEMMs of another.
         C = args.chains_per_gpu
-        sims = [sim] + [im.Simulation(n_layers=K, n_samples=8, n=cfg["n"], n_extended=cfg["n_ext"], beta=0.3, kappa=5e9, sigma_0=4e7,
+        sims = [sim] + [im.Simulation(n_layers=K, n_samples=8, n=cfg["n"], n_extended=cfg["n_ext"], beta=BENCH_BETA, kappa=5e9, sigma_0=4e7,
                                       sigma_v=3.2e4, sigma_scaling=0.4, meas_std=0.2, evaluation_interval=10, printProgress=False,
                                       seed=100 + rank * C + c, burn_percentage=25.0, enable_step_adaptation=True,
                                       pcn_variant="dunlop", phantom_name="shepp.png", meas_type="tomo", n_theta=cfg["n_theta"],
@@ -463,8 +546,7 @@ def main():
                                          if gemm_mode == _ffi.GEMM_3M else
                                          "profiles/r01_zgemm_full_v2.ncu-rep (grouped tile rasterisation; 56.2e9 before it)"),
                     "ms_per_launch": ms_k,
-                    "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_fp64_probe.log); "
-                                   "MEASURED_PEAKS.json has no FP64 entry",
+                    "peak_source": fp64_peak_source,
                     "step_fp64": {"flops_per_step": f_iter, "achieved": step_rate, "frac": step_rate / FP64_PEAK_TFLOPS,
                                   "executed_frac": executed * step_rate / FP64_PEAK_TFLOPS,
                                   "note": "flops_per_step is SURVEY 8(d)'s F_iter (8-flop convention); executed_frac scales it by the "
@@ -502,9 +584,20 @@ def main():
              "bytes": 8.0 * M * M, "achieved": 8.0 * M * M / ms_v * 1e-6, "peak": hbm_peak, "unit": "GB/s",
              "frac": 8.0 * M * M / ms_v * 1e-6 / hbm_peak, "peak_source": hbm_src}]
 
+    library = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            ms_lib = library_standin_ms(sim, to_dev(noises[0]))
+            library = {"ms_per_step": ms_lib, "value": 1e3 / ms_lib, "unit": "iters/s", "speedup_of_ours": ms_lib / (ms_dev / args.steps),
+                       "what": "the same iteration through library calls only (torch.fft = cuFFT, @ = cuBLAS ZGEMM, torch.linalg = "
+                               "cuSOLVER), same inputs, same process: the stand-in for the reference's CuPy path on this box"}
+        except Exception as ex:
+            library = {"unavailable": repr(ex)[:200]}
+        torch.cuda.empty_cache()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, desc, cores, dt = cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=30.0)
+        rate, desc, cores, dt, done = cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=30.0)
         cpu_baseline = {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": desc}
 
     if rank == 0:
@@ -514,6 +607,7 @@ def main():
                 "config": workload_config(cfg, world),
                 "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "library_standin": library,
                 "gemm_scheme": "3m" if gemm_mode == _ffi.GEMM_3M else "4m", "acceptance_rate": acc_rate, "setup_s": t_setup}
         line.update(extra)
         emit(line)

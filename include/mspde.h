@@ -21,6 +21,9 @@ extern "C" {
 typedef struct mspde_ctx mspde_ctx;
 
 const char* mspde_last_error(void);
+/* FP64 tensor-pipe (DMMA m8n8k4) peak of the current device in TFLOP/s, measured now (~0.3 s; synchronises).  bench.py uses it
+ * as the roofline denominator of the box it runs on (MEASURED_PEAKS.json carries no FP64 figure). */
+int mspde_fp64_peak_probe(void* stream, double* tflops_host);
 long long mspde_launch_count(void);   /* kernels launched by the library so far (bench.py gpu_launches) */
 
 /* Complex product scheme of every dense contraction of the path (the cuBLAS ZGEMM calls behind `@`, cp.linalg.solve,
@@ -98,7 +101,10 @@ typedef struct {
     void** L_cur;                   /* per layer k >= 1: N x ldl; entry 0 unused */
     void** L_latest;
     int ldl;
-    int phi_cur_valid;              /* scal cache holds Phi(L_cur[last]) from a previous step */
+    int phi_cur_valid;              /* phi_cache holds Phi(L_cur[last]) from a previous step of THIS chain, computed with the
+                                       context's current inputs and the same Phi flavour (the host tracks both) */
+    double* phi_cache;              /* device, 3 doubles owned by the chain: {Phi, quad, logdet} of L_cur[last]; NULL = a
+                                       context-owned slot (one chain per context only) */
 } mspde_chain;
 
 typedef struct {

@@ -189,7 +189,7 @@ int pcn_step(Ctx* c, const mspde_chain* ch, const mspde_step_noise* nz, int flag
     c->stream = st;
     const int K = ch->n_layers, N = c->N, M = c->M, nr = c->n_ravel;
     const int nb = (N + 255) / 256;
-    double* phi_cur3 = c->scal + 8;
+    double* phi_cur3 = ch->phi_cache ? ch->phi_cache : c->scal + 8;   // per-chain cache of Phi(L_cur[last])
     double* phi_new3 = c->scal + 12;
     cplx* cand_acc = c->vecN;
     cplx* cand_rej = c->vecN + N;

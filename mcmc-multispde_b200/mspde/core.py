@@ -27,7 +27,7 @@ class _Chain(ctypes.Structure):
                 ("noise_cur", ctypes.POINTER(ctypes.c_void_p)), ("noise_new", ctypes.POINTER(ctypes.c_void_p)),
                 ("u_cur", ctypes.POINTER(ctypes.c_void_p)), ("u_new", ctypes.POINTER(ctypes.c_void_p)),
                 ("L_cur", ctypes.POINTER(ctypes.c_void_p)), ("L_latest", ctypes.POINTER(ctypes.c_void_p)),
-                ("ldl", ctypes.c_int), ("phi_cur_valid", ctypes.c_int)]
+                ("ldl", ctypes.c_int), ("phi_cur_valid", ctypes.c_int), ("phi_cache", ctypes.c_void_p)]
 
 
 class _StepNoise(ctypes.Structure):
@@ -64,6 +64,7 @@ class MspdeContext:
                                                 1 if assembly_only else 0), "mspde_ctx_create")
         self._keep = {}
         self.scal = torch.zeros(16, dtype=torch.float64, device=self.device)
+        self.generation = 0          # bumped whenever H / y / delta / stdev_sym change: invalidates every chain's cached Phi
 
     def close(self):
         if self._h:
@@ -99,6 +100,7 @@ class MspdeContext:
         sd = self.to_dev(stdev_sym, torch.float64)
         self._keep.update(H=Hd, Hct=Hct, HtH=HtHd, y=yd, D=Dd, stdev=sd)
         self.H, self.Hct, self.HtH, self.y, self.D_diag, self.stdev_sym, self.delta = Hd, Hct, HtHd, yd, Dd, sd, float(delta)
+        self.generation += 1
         _ffi.check(self.lib.mspde_ctx_set_inputs(self._h, _ffi.ptr(Hd), Hd.stride(0), _ffi.ptr(Hct), Hct.stride(0),
                                                  _ffi.ptr(HtHd), HtHd.stride(0), _ffi.ptr(yd), _ffi.ptr(Dd), _ffi.ptr(sd),
                                                  c_double(float(delta))), "mspde_ctx_set_inputs")
@@ -110,6 +112,7 @@ class MspdeContext:
             self._keep["stdev"] = self.stdev_sym
         if delta is not None:
             self.delta = float(delta)
+        self.generation += 1
         _ffi.check(self.lib.mspde_ctx_set_inputs(self._h, _ffi.ptr(self.H), self.H.stride(0), _ffi.ptr(self.Hct),
                                                  self.Hct.stride(0), _ffi.ptr(self.HtH), self.HtH.stride(0), _ffi.ptr(self.y),
                                                  _ffi.ptr(self.D_diag), _ffi.ptr(self.stdev_sym), c_double(self.delta)),
@@ -194,12 +197,16 @@ class MspdeContext:
         self._sync_stream()
         K = self.n_layers
         out = torch.empty(4, dtype=torch.float64, device=self.device) if out is None else out
+        # the cached Phi(L_cur) is only reusable for the same inputs and the same Phi formulation
+        tag = (self.generation, int(flags) & (STEP_FAST_PHI | STEP_NAIVE_PHI))
+        if chain.phi_cache_tag != tag:
+            chain.phi_cur_valid = 0
         cs = chain.as_struct()
         wh = _ptr_array(list(w_half))
         nz = _StepNoise(ctypes.cast(wh, ctypes.POINTER(ctypes.c_void_p)), w_last.data_ptr(), e.data_ptr(), float(log_u))
         _ffi.check(self.lib.mspde_pcn_step(self._h, ctypes.byref(cs), ctypes.byref(nz), int(flags), _ffi.ptr(out),
                                            _ffi.ptr(record)), "pcn_step")
-        chain.phi_cur_valid = 1
+        chain.phi_cur_valid, chain.phi_cache_tag = 1, tag
         return out
 
     def posterior_stats_update(self, u_sym, count: int, stats: dict):
@@ -256,7 +263,13 @@ class ChainBuffers:
         self.sqrt_betas = [float(s) for s in sqrt_betas]
         self._sb = (c_double * K)(*self.sqrt_betas)
         self.phi_cur_valid = 0
+        self.phi_cache = torch.zeros(4, dtype=torch.float64, device=ctx.device)   # per-chain {Phi, quad, logdet} of L_cur
+        self.phi_cache_tag = None
         self.set_step(beta)
+
+    def invalidate_phi_cache(self):
+        """Call after writing L_cur from outside pcn_step (e.g. the sqrt-beta move promotes a new current_L)."""
+        self.phi_cur_valid = 0
 
     def set_step(self, beta: float):
         self.beta = float(beta)
@@ -268,4 +281,4 @@ class ChainBuffers:
                                               self.L_latest)]
         casted = [ctypes.cast(a, ctypes.POINTER(ctypes.c_void_p)) for a in self._arrs]
         return _Chain(K, self.beta, self.betaZ, ctypes.cast(self._sb, ctypes.POINTER(c_double)), *casted,
-                      self.L_cur[1].stride(0), self.phi_cur_valid)
+                      self.L_cur[1].stride(0), self.phi_cur_valid, self.phi_cache.data_ptr())

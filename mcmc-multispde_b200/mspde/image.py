@@ -8,6 +8,7 @@ CPU fallback.  Setup-only pieces (tomography matrix, phantom, sinogram) are nump
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 import pathlib
@@ -362,6 +363,14 @@ class pCN:
             self.beta = float(newBeta)
             self.betaZ = math.sqrt(1 - self.beta ** 2)
 
+    def set_step_sqrtBeta(self, newStep):                                           # 542-544
+        self.pcn_step_sqrtBetas = min(1., newStep)
+        self.pcn_step_sqrtBetas_Z = math.sqrt(1 - self.pcn_step_sqrtBetas ** 2)
+
+    def adapt_step_sqrtBeta(self, current_acceptance_rate):                         # 546-548
+        self.set_step_sqrtBeta(self.pcn_step_sqrtBetas * math.exp(self.beta_feedback_gain * (current_acceptance_rate
+                                                                                             - self.target_acceptance_rate)))
+
     # -- Phi (618-662) -------------------------------------------------------------------------------------
     def _log_ratio(self, L):
         self._ensure_inputs()
@@ -376,12 +385,14 @@ class pCN:
             cb.noise_new = [l._noise_new for l in Layers]
             cb.u_cur = [l._u_cur for l in Layers]
             cb.u_new = [l._u_new for l in Layers]
-            cb.sqrt_betas = [float(l.sqrt_beta) for l in Layers]
-            import ctypes
-            cb._sb = (ctypes.c_double * len(Layers))(*cb.sqrt_betas)
-            cb.phi_cur_valid = 0
+            cb.phi_cur_valid, cb.phi_cache_tag = 0, None
+            cb.phi_cache = torch.zeros(4, dtype=torch.float64, device=self.ctx.device)
             self._chain, self._chain_layers = cb, Layers
         cb = self._chain
+        # The assembly divides by Lmatrix_2D.sqrt_beta (image_cupy.py:179), which is fixed at construction (161-163): an
+        # accepted sqrt-beta move changes Layer.sqrt_beta (704) but NOT what construct_from uses.  Reproduced as is.
+        cb.sqrt_betas = [float(l.LMat.sqrt_beta) for l in Layers]
+        cb._sb = (ctypes.c_double * len(Layers))(*cb.sqrt_betas)
         # L buffers can be re-pointed by set_current_L_to_latest / construct_from: refresh every step
         for l in Layers[1:]:
             l._ensure_two_L_buffers()
@@ -391,24 +402,28 @@ class pCN:
         return cb
 
     def _draw_noise(self):
-        """RNG call order of the reference (558, 573, 583, 585)."""
+        """RNG call order of the reference (558, 573, 583, 585); a noise source may add a "move" entry (dict z, e, log_u:
+        the draws of one_step_for_sqrtBetas, 668, 684, 699)."""
         if self.noise_source is not None:
             nz = self.noise_source.draw_iteration()
             dev = self.ctx.to_dev
-            return [dev(w) for w in nz["w_half"]], float(nz["log_u"]), dev(nz["w_last"]), dev(nz["e"])
+            return [dev(w) for w in nz["w_half"]], float(nz["log_u"]), dev(nz["w_last"]), dev(nz["e"]), nz.get("move")
         rg = self.random_gen
         w = [rg.construct_w_Half() for _ in range(self.n_layers - 1)]
         log_u = math.log(float(torch.rand(1, dtype=torch.float64, device=self.ctx.device, generator=rg.gen).item()))
         w_last = rg.construct_w_Half()
         e = torch.randn(self.measurement.num_sample, dtype=torch.float64, device=self.ctx.device, generator=rg.gen)
-        return w, log_u, w_last, e
+        return w, log_u, w_last, e, None
 
     def one_step(self, Layers, noise=None):
         """Returns (accepted, accepted_SqrtBeta) like the reference; raises numpy.linalg.LinAlgError when a
-        Cholesky factorisation fails (the only error Simulation.run catches, 969)."""
+        Cholesky factorisation fails (the only error Simulation.run catches, 969).
+        noise: (w_half list, log_u, w_last, e[, move]) device tensors to inject, else the noise source / device RNG."""
         self._ensure_inputs(Layers[0].stdev_sym_host)
         cb = self._bind(Layers)
-        w_half, log_u, w_last, e = noise if noise is not None else self._draw_noise()
+        nz = tuple(noise) if noise is not None else self._draw_noise()
+        w_half, log_u, w_last, e = nz[:4]
+        move_noise = nz[4] if len(nz) > 4 else None
         flags = ((STEP_CACHE_PHI_CUR if self.cache_phi_current else 0) | (STEP_SKIP_GIBBS if self.skip_gibbs else 0)
                  | (STEP_FAST_PHI if self.fast_phi else 0) | (STEP_NAIVE_PHI if self.use_naive_logRatio_implementation else 0))
         do_record = (self.record_count % self.record_skip) == 0
@@ -421,6 +436,9 @@ class pCN:
         accepted = int(self._out_host[0].item())
         self.last_step = dict(accepted=accepted, log_ratio=float(self._out_host[1]), phi_cur=float(self._out_host[2]),
                               phi_new=float(self._out_host[3]), log_u=log_u)
+        # 604-607: the hyper-move runs BEFORE the record (609-613); it changes sqrt_beta / current_L / stdev_sym but not the
+        # current samples, so the half-samples copied out by the fused step are still what record_sample must store.
+        accepted_SqrtBeta = self.one_step_for_sqrtBetas(Layers, noise=move_noise) if self.use_beta_adaptation else 0
         if do_record:
             for k, l in enumerate(Layers):
                 l.record_sample(self._rec_host[k].numpy())
@@ -431,7 +449,6 @@ class pCN:
                     l.stats["count"] += 1
                     self.ctx.posterior_stats_update(l._u_cur, l.stats["count"], l.stats)
         self.record_count += 1
-        accepted_SqrtBeta = self.one_step_for_sqrtBetas(Layers) if self.use_beta_adaptation else 0      # 604-607
         return accepted, accepted_SqrtBeta
 
     # -- optional hyper-parameter move (666-710) ------------------------------------------------------------
@@ -479,10 +496,7 @@ class pCN:
                 else:
                     Layers[i].stdev_sym = stdev_sym_temp
             if self._chain is not None:
-                self._chain.sqrt_betas = [float(l.sqrt_beta) for l in Layers]
-                import ctypes
-                self._chain._sb = (ctypes.c_double * K)(*self._chain.sqrt_betas)
-                self._chain.phi_cur_valid = 0
+                self._chain.invalidate_phi_cache()      # current_L of the last layer was replaced
         self.last_sqrt_beta_step = dict(accepted=accepted, log_ratio=log_ratio, phi_cur=phi_cur, phi_new=phi_new, prop=prop)
         return accepted
 
@@ -682,12 +696,14 @@ class Simulation:
         start_time_intv = start_time
         average_time_intv = 0.0
         accepted_count_partial = 0
+        accepted_count_partial_SqrtBeta = 0
         linalg_error_occured = False
         i = 0
         for i in range(self.n_samples):
             try:
                 accepted, accepted_SqrtBeta = self.pcn.one_step(self.Layers)
                 accepted_count_partial += accepted
+                accepted_count_partial_SqrtBeta += accepted_SqrtBeta
             except np.linalg.LinAlgError as err:
                 linalg_error_occured = True
                 print("Linear Algebra Error :", err)
@@ -695,10 +711,13 @@ class Simulation:
             else:
                 if (i + 1) % self.evaluation_interval == 0:
                     self.accepted_count += accepted_count_partial
+                    self.accepted_count_SqrtBeta += accepted_count_partial_SqrtBeta
                     self.acceptancePercentage = self.accepted_count / (i + 1)
-                    if self.enable_step_adaptation:
+                    if self.enable_step_adaptation:                                               # 977-979
                         self.pcn.adapt_step(self.acceptancePercentage)
+                        self.pcn.adapt_step_sqrtBeta(self.accepted_count_SqrtBeta / (i + 1))
                     accepted_count_partial = 0
+                    accepted_count_partial_SqrtBeta = 0
                     mTime = (i + 1) / self.evaluation_interval
                     end_time_intv = time.time()
                     average_time_intv += (end_time_intv - start_time_intv - average_time_intv) / mTime
@@ -709,10 +728,11 @@ class Simulation:
                                               prefix='Time Remaining {0:.0f}s- Acceptance Rate {1:.2%} - Progress:'.format(
                                                   remaining, self.acceptancePercentage), suffix='Complete', length=50)
         if linalg_error_occured:
-            end_index = max(i % self.pcn.record_skip, 1)
-            for l in range(self.n_layers):
-                self.Layers[l].samples_history = self.Layers[l].samples_history[:end_index, :]
-            print('Linear algebra errors occured during some simulation step(s). The simulation result may not be valid')
+            if self.printProgress:                                                                # 998-1004 (only when printing)
+                end_index = max(i % self.pcn.record_skip, 1)
+                for l in range(self.n_layers):
+                    self.Layers[l].samples_history = self.Layers[l].samples_history[:end_index, :]
+                print('Linear algebra errors occured during some simulation step(s). The simulation result may not be valid')
         else:
             self.total_time = time.time() - start_time
 

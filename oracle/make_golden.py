@@ -112,5 +112,32 @@ def main():
     print("goldens written to", OUT)
 
 
+def config2_golden(steps=2):
+    """4. oracle_config2_n32.npz : BASELINE configs[1] (n=32, n_ext=64, 90 angles, 3 layers) -- two whole oracle iterations
+    (25-40 s of CPU each), so the GPU test can compare the full-size CUDA step with the oracle itself and not only with a
+    cuSOLVER rendition.  Inputs are regenerated on the GPU box by the same deterministic oracle calls (seconds); the golden
+    stores the expensive outputs: Phi pair, accept flag, log-ratio margin, the three half-samples, the Gibbs draw."""
+    hp = o.Hyper(n_layers=3, n=32, n_ext=64, n_theta=90, beta=0.25)
+    pb = o.synthetic_problem(hp)
+    ft, H, HtH, y, delta = pb["ft"], pb["H"], pb["HtH"], pb["y"], pb["delta"]
+    ns = o.NoiseStream(32, 3, ft.n_ravel, H.shape[0])
+    st = o.init_chain(hp, ft, [ns.half() for _ in range(3)], [ns.half() for _ in range(3)])
+    out = []
+    for it in range(steps):
+        d = o.one_step(st, ft, H, HtH, y, delta, ns.draw_iteration())
+        d["halves"] = np.stack(o.current_halves(st, ft))
+        d["u_new"] = np.stack([u.copy() for u in st.u_new_sym])
+        print("config2 step", it, {k: v for k, v in d.items() if np.isscalar(v)}, flush=True)
+        out.append(d)
+    np.savez_compressed(os.path.join(OUT, "oracle_config2_n32.npz"), seed=32, beta=0.25, y_checksum=np.array([y.sum(), np.abs(y).sum()]),
+                        delta=delta, accepted=np.array([s["accepted"] for s in out]), phi_cur=np.array([s["phi_cur"] for s in out]),
+                        phi_new=np.array([s["phi_new"] for s in out]), log_u=np.array([s["log_u"] for s in out]),
+                        log_ratio=np.array([s["log_ratio"] for s in out]), halves=np.stack([s["halves"] for s in out]),
+                        u_new=np.stack([s["u_new"] for s in out]))
+
+
 if __name__ == "__main__":
-    main()
+    if "--config2" in sys.argv:
+        config2_golden()
+    else:
+        main()

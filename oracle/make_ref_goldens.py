@@ -1,0 +1,264 @@
+"""Golden vectors from the REFERENCE'S OWN Python (run in this container only; needs /root/reference).
+
+    python oracle/make_ref_goldens.py              # all cases, both precision modes (each in its own subprocess)
+    python oracle/make_ref_goldens.py --case n4 --mode alias
+
+Imports ``/root/reference/mcmc/image_cupy.py`` unmodified through ``oracle/ref_shim.py`` (numpy stands in for CuPy,
+numba's CUDA simulator runs the two ``numba.cuda`` kernels verbatim) and runs, with the reference's own call order and
+a logged PCG64 noise stream:
+
+  * ``Simulation.__init__`` (image_cupy.py:810-946): Fourier tables, prior tables, H (the reference's own
+    ``_calculate_H_Tomography`` kernel + post-fixes), ``pCN.__init__`` normalisation, ``Layer.__init__`` for every layer;
+  * ``pCN.set_chol_epsilon`` (473-478) as the driver does (twoDsim.py:106);
+  * ``FourierAnalysis_2D.irfft2 / rfft2`` coefficient tables and ``Lmatrix_2D.construct_from`` (108-149, 171-196);
+  * ``Lmatrix_2D.logDet`` (268-276), ``pCN._log_ratio`` default and naive (618-662), ``util.lstsq`` (util_cupy.py:590-609);
+  * S steps of ``pCN.one_step`` (553-617), then ``pCN.adapt_step`` (528-540), then steps of ``pCN.one_step`` with
+    ``use_beta_adaptation`` = ``one_step_for_sqrtBetas`` (666-710), ``Layer.record_sample`` histories (792-799);
+  * ``Simulation.save`` -> ``util._save_object`` (util_cupy.py:553-583) into a recording h5py stand-in (key layout);
+  * ``twoDsim.initialize_using_FBP`` (twoDsim.py:25-34), AST-extracted (the driver module itself imports plotting code).
+
+Output: ``tests/golden/ref_step_{case}_{mode}.npz`` (+ ``ref_save_layout.json``).  ``mode`` = ``alias`` (complex64 ->
+complex128, float32 -> float64: the reference's semantics in FP64, compared at 1e-12 by the CPU test and 1e-10 by the
+GPU test) or ``native`` (the reference's own mixed precision, compared at ~1e-4: documents SURVEY Appendix A.3).
+"""
+from __future__ import annotations
+
+import argparse
+import ast
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+
+# case -> (n, n_ext, n_theta, n_layers, beta, seed, n_plain_steps, n_sqrtbeta_steps, store_matrices)
+CASES = {
+    "n2": (2, 64, 8, 3, 0.5, 3, 4, 2, True),
+    "n3": (3, 64, 8, 3, 0.7, 5, 4, 2, True),
+    "n4": (4, 64, 8, 3, 0.5, 7, 6, 2, True),
+    "n4k2": (4, 64, 8, 2, 1.0, 11, 3, 0, True),      # 2 layers, beta=1 (the driver default: independence proposals)
+    "n4k4": (4, 64, 8, 4, 0.4, 8, 3, 2, False),      # 4 layers: two middle layers
+    "n8": (8, 64, 8, 3, 0.5, 9, 3, 1, False),
+    "n16": (16, 64, 45, 2, 0.5, 1, 2, 0, False),     # BASELINE configs[0] geometry (2 layers, 45 angles)
+}
+
+
+def checksum(a):
+    import numpy as np
+    a = np.asarray(a)
+    w = np.cos(np.arange(a.size, dtype=np.float64) * 0.37).reshape(a.shape)  # position-sensitive weights
+    return np.array([a.real.sum(), a.imag.sum() if np.iscomplexobj(a) else 0.0, np.abs(a).sum(),
+                     (a.real * w).sum(), ((a.imag if np.iscomplexobj(a) else 0 * a.real) * w).sum()])
+
+
+def run_case(case: str, mode: str):
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+    n, n_ext, n_theta, K, beta, seed, n_steps, n_sb_steps, store_mats = CASES[case]
+    alias = mode == "alias"
+    work = tempfile.mkdtemp(prefix="refgold_")
+    os.chdir(work)
+    ns = ref_shim.install(alias64=alias, seed=seed)
+    im, util, cp, rnd = ns.im, ns.util, ns.cp, ns.random
+    c128 = np.complex128
+
+    if n >= 16:
+        # The reference caches H under ./matrices (image_cupy.py:480-508) and loads it when present.  Running its
+        # tomography kernel body for 5.5 M entries under the CUDA simulator takes ~30 min, so for this one case the cache is
+        # pre-filled from the oracle's closed form (itself pinned to that kernel body, tests/golden/ref_H_tomography.npz).
+        from oracle import mspde_oracle as o
+        ft = o.FourierTables(n, n_ext)
+        H0 = o.tomography_H(ft, n_theta)
+        t = H0.conj().T @ H0
+        theta = np.linspace(0., 180., n_theta, endpoint=False)
+        os.makedirs("matrices", exist_ok=True)
+        name = 'radon_matrix_Four_Basis{}_Image_size {}_[{},{}]N_theta{}_{}.npz'.format(n, 2 * n_ext - 1, theta[0], theta[-1], n_theta, "F")
+        np.savez_compressed(os.path.join("matrices", name), H=H0.astype(cp.complex64), H_t_H=(0.5 * (t + t.conj().T)).astype(cp.complex64))
+
+    t0 = time.time()
+    sim = im.Simulation(n_layers=K, n_samples=n_steps + n_sb_steps + 2, n=n, n_extended=n_ext, beta=beta, kappa=5e9, sigma_0=4e7,
+                        sigma_v=3.2e4, sigma_scaling=0.4, meas_std=0.2, evaluation_interval=10, printProgress=False, seed=seed,
+                        burn_percentage=25.0, enable_step_adaptation=True, pcn_variant="dunlop", phantom_name="shepp.png",
+                        meas_type="tomo", n_theta=n_theta, verbose=False, hybrid_GPU_CPU=False)
+    sim.pcn.set_chol_epsilon(1e-6)                      # twoDsim.py:106
+    sim.pcn.target_acceptance_rate = 0.234
+    pcn, f, Ls = sim.pcn, sim.fourier, sim.Layers
+    if alias:
+        # sqrt_beta scalars were rounded by .astype('float32') (846-847) and are float32-TYPED, which makes the hyper-move take
+        # log() in single precision (673).  FP64 semantics: keep the rounded VALUE (an input table), drop the 32-bit type.
+        for l in Ls:
+            l.sqrt_beta = np.float64(l.sqrt_beta)
+            l.LMat.sqrt_beta = np.float64(l.LMat.sqrt_beta)
+    init_draws = rnd.take_log()
+    print(f"[{case}/{mode}] Simulation built in {time.time() - t0:.1f}s, H {pcn.H.shape} {pcn.H.dtype}, L {Ls[-1].LMat.current_L.dtype}",
+          flush=True)
+    nr = f.basis_number_2D_ravel
+    g = dict(case=case, mode=mode, n=n, n_ext=n_ext, n_theta=n_theta, n_layers=K, beta0=float(pcn.beta), betaZ0=float(pcn.betaZ),
+             seed=seed, meas_std=0.2, chol_epsilon=1e-6, kappa=5e9, sigma_0=4e7, sigma_v=3.2e4, sigma_scaling=0.4)
+    # ---- a1 / a14: tables and fixed inputs as the reference built them
+    g["ix"], g["iy"], g["Kmatrix"] = np.asarray(f.ix), np.asarray(f.iy), np.asarray(f.Kmatrix)
+    g["D_diag"] = np.asarray(f.D_diag, dtype=np.float64)
+    g["sqrt_betas"] = np.array([float(l.sqrt_beta) for l in Ls])
+    g["lmat_sqrt_betas"] = np.array([float(l.LMat.sqrt_beta) for l in Ls])
+    g["stdev_sym"] = np.asarray(Ls[0].stdev_sym, dtype=np.float64)
+    g["y"] = np.asarray(pcn.y, dtype=np.float64)
+    g["delta"] = float(pcn.cholesky_stabilizer)
+    g["sinogram"] = np.asarray(sim.measurement.sinogram, dtype=np.float64)
+    g["theta"] = np.asarray(sim.measurement.theta, dtype=np.float64)
+    H, HtH = np.asarray(pcn.H).astype(c128), np.asarray(pcn.H_t_H).astype(c128)
+    g["H_checksum"], g["HtH_checksum"] = checksum(H), checksum(HtH)
+    rows = np.unique(np.linspace(0, H.shape[0] - 1, 12).astype(int))
+    g["H_rows_idx"], g["H_rows"] = rows, H[rows]
+    if store_mats:
+        g["H"], g["HtH"] = H, HtH
+    # ---- initial chain state (Layer.__init__ + Simulation.__init__ 902-946)
+    for k, l in enumerate(Ls):
+        g[f"init_noise_cur_{k}"] = np.asarray(l.current_noise_sample).astype(c128)
+        g[f"init_u_cur_{k}"] = np.asarray(l.current_sample_sym).astype(c128)
+        g[f"init_u_new_{k}"] = np.asarray(l.new_sample_sym).astype(c128)
+        if k >= 1:
+            Lc = np.asarray(l.LMat.current_L).astype(c128)
+            g[f"init_L_checksum_{k}"] = checksum(Lc)
+            g[f"init_logdet_{k}"] = float(l.LMat.logDet(False))          # a5, image_cupy.py:268-276
+            if store_mats:
+                g[f"init_L_{k}"] = Lc
+    g["init_draws"] = np.concatenate([np.atleast_1d(a).ravel() for _, a in init_draws])
+    g["init_draw_sizes"] = np.array([np.atleast_1d(a).size for _, a in init_draws])
+    # ---- a2: coefficient tables of the reference's own irfft2 / exp / rfft2 (139-145), from layer K-2's current sample
+    uh = util.from_u_2D_ravel_to_uHalf_2D(Ls[K - 2].current_sample_sym, f.basis_number)
+    img = f.irfft2(uh)
+    g["a2_u_sym"] = np.asarray(Ls[K - 2].current_sample_sym).astype(c128)
+    g["a2_image"] = np.asarray(img, dtype=np.float64)
+    g["a2_table_plus"] = np.asarray(util.symmetrize_2D(f.rfft2(util.kappa_pow_min_nu(img)))).astype(c128)
+    g["a2_table_minus"] = np.asarray(util.symmetrize_2D(f.rfft2(util.kappa_pow_d_per_2(img)))).astype(c128)
+    # ---- a9: Phi of the initial last-layer L, default and naive branch; a11: lstsq on the stacked matrix
+    Lc = Ls[-1].LMat.current_L
+    g["phi_init"] = float(pcn._log_ratio(Lc))
+    pcn.use_naive_logRatio_implementation = True
+    try:
+        g["phi_init_naive"] = float(pcn._log_ratio(Lc))
+    except np.linalg.LinAlgError:
+        g["phi_init_naive"] = np.nan                                     # the unstabilised Cholesky (656) can fail
+    pcn.use_naive_logRatio_implementation = False
+    rng = np.random.default_rng(100 + seed)
+    rhs = rng.standard_normal(H.shape[0] + f.basis_number_2D_sym) + 1j * rng.standard_normal(H.shape[0] + f.basis_number_2D_sym)
+    g["lstsq_rhs"] = rhs
+    g["lstsq_x"] = np.asarray(util.lstsq(cp.vstack((pcn.H, Lc)), rhs)[0]).astype(c128)
+    rnd.take_log()
+
+    # ---- instrument _log_ratio (bound-method wrapper: records what the reference computed, changes nothing)
+    phis = []
+    orig = pcn._log_ratio
+
+    def rec_log_ratio(L):
+        v = orig(L)
+        phis.append(float(v))
+        return v
+    pcn._log_ratio = rec_log_ratio
+
+    def snapshot(prefix):
+        for k, l in enumerate(Ls):
+            g[f"{prefix}_noise_new_{k}"] = np.asarray(l.new_noise_sample).astype(c128)
+            g[f"{prefix}_noise_cur_{k}"] = np.asarray(l.current_noise_sample).astype(c128)
+            g[f"{prefix}_u_new_{k}"] = np.asarray(l.new_sample_sym).astype(c128)
+            g[f"{prefix}_u_cur_{k}"] = np.asarray(l.current_sample_sym).astype(c128)
+            if k >= 1:
+                g[f"{prefix}_L_latest_checksum_{k}"] = checksum(np.asarray(l.LMat.latest_computed_L).astype(c128))
+                g[f"{prefix}_L_cur_checksum_{k}"] = checksum(np.asarray(l.LMat.current_L).astype(c128))
+
+    def store_draws(prefix):
+        d = rnd.take_log()
+        g[f"{prefix}_draws"] = np.concatenate([np.atleast_1d(a).ravel() for _, a in d])
+        g[f"{prefix}_draw_sizes"] = np.array([np.atleast_1d(a).size for _, a in d])
+        g[f"{prefix}_draw_kinds"] = np.array([0 if kd == "randn" else 1 for kd, _ in d])
+
+    accepted, betas = [], []
+    total = 0
+    for s in range(n_steps):
+        t0 = time.time()
+        phis.clear()
+        acc, acc_sb = pcn.one_step(Ls)                                   # image_cupy.py:553-617
+        store_draws(f"s{s}")
+        snapshot(f"s{s}")
+        g[f"s{s}_phi"] = np.array(phis)                                  # [Phi(L_cur), Phi(L_latest)]
+        accepted.append(int(acc))
+        total += int(acc)
+        betas.append(float(pcn.beta))
+        print(f"[{case}/{mode}] step {s}: accepted={acc} phi={phis} ({time.time() - t0:.1f}s)", flush=True)
+        if s == n_steps // 2:
+            pcn.adapt_step(total / (s + 1))                              # 528-540 (what Simulation.run does at 977-979)
+            g["adapt_after_step"], g["adapt_rate"] = s, total / (s + 1)
+            g["adapt_beta"], g["adapt_betaZ"] = float(pcn.beta), float(pcn.betaZ)
+    g["accepted"] = np.array(accepted)
+    g["beta_used"] = np.array(betas)
+    # ---- a15: the sqrt-beta hyper-move inside one_step (604-607 -> 666-710)
+    pcn.use_beta_adaptation = True
+    acc_sb_list, acc_list = [], []
+    for s in range(n_sb_steps):
+        phis.clear()
+        acc, acc_sb = pcn.one_step(Ls)
+        store_draws(f"b{s}")
+        snapshot(f"b{s}")
+        g[f"b{s}_phi"] = np.array(phis)                                  # [plain cur, plain new, move cur, move new]
+        g[f"b{s}_sqrt_betas"] = np.array([float(l.sqrt_beta) for l in Ls])
+        g[f"b{s}_stdev_sym"] = np.asarray(Ls[0].stdev_sym, dtype=np.float64)
+        acc_list.append(int(acc))
+        acc_sb_list.append(int(acc_sb))
+        print(f"[{case}/{mode}] sqrt-beta step {s}: accepted={acc} accepted_sqrtbeta={acc_sb} phi={phis}", flush=True)
+    g["b_accepted"], g["b_accepted_sqrtbeta"] = np.array(acc_list), np.array(acc_sb_list)
+    g["pcn_step_sqrtBetas"] = float(pcn.pcn_step_sqrtBetas)
+    g["beta_final"] = float(pcn.beta)
+    pcn.use_beta_adaptation = False
+    pcn._log_ratio = orig
+    del pcn.__dict__["_log_ratio"]
+    # ---- a12: recorded histories (complex64 host arrays, 729/939)
+    for k, l in enumerate(Ls):
+        g[f"history_{k}"] = np.asarray(l.samples_history[:l.i_record])
+        g[f"sqrt_beta_history_{k}"] = np.asarray(l.sqrt_beta_history[:l.i_record + 1])
+    # ---- f3: FBP initialisation of the driver (twoDsim.py:25-34), function body executed verbatim
+    src = open(os.path.join(REF, "twoDsim.py")).read()
+    fn = [nd for nd in ast.parse(src).body if isinstance(nd, ast.FunctionDef) and nd.name == "initialize_using_FBP"][0]
+    from skimage.transform import iradon
+    env = dict(iradon=iradon, cp=cp, util=util, im=im)
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "twoDsim.py", "exec"), env)
+    rec_before = Ls[-1].i_record
+    env["initialize_using_FBP"](sim)
+    g["fbp_image"] = np.asarray(iradon(np.asarray(sim.measurement.sinogram), theta=np.asarray(sim.measurement.theta), circle=True))
+    g["fbp_sym"] = np.asarray(Ls[-1].current_sample_sym).astype(c128)
+    g["fbp_recorded"] = int(Ls[-1].i_record - rec_before)
+    # ---- f3: the key layout Simulation.save writes (util_cupy.py:553-583)
+    if case == "n4" and not alias:
+        sim.total_time = 0.0
+        sim.save("result_0.hdf5")
+        layout = ns.RecordingFile.last.layout()
+        with open(os.path.join(OUT, "ref_save_layout.json"), "w") as fh:
+            json.dump({k: dict(dtype=v["dtype"], shape=list(v["shape"]), compression=v["compression"]) for k, v in sorted(layout.items())},
+                      fh, indent=1)
+    np.savez_compressed(os.path.join(OUT, f"ref_step_{case}_{mode}.npz"), **g)
+    print(f"[{case}/{mode}] wrote ref_step_{case}_{mode}.npz", flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default=None)
+    ap.add_argument("--mode", default=None, choices=[None, "alias", "native"])
+    args = ap.parse_args()
+    if args.case and args.mode:
+        run_case(args.case, args.mode)
+        return
+    env = dict(os.environ, NUMBA_ENABLE_CUDASIM="1", NUMBA_CACHE_DIR="/tmp/nbcache")
+    for case in ([args.case] if args.case else CASES):
+        for mode in ([args.mode] if args.mode else ["alias", "native"]):
+            if mode == "native" and case in ("n16", "n4k4"):
+                continue
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--case", case, "--mode", mode], check=True, env=env)
+
+
+if __name__ == "__main__":
+    main()

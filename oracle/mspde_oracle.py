@@ -389,6 +389,9 @@ class ChainState:
     L_latest: list
     accepted_total: int = 0
     iteration: int = 0
+    # Lmatrix_2D.sqrt_beta per layer: fixed at construction (image_cupy.py:161-163) and the value construct_from divides by
+    # (179), even after an accepted sqrt-beta move has changed Layer.sqrt_beta (703-704).  None = same as sqrt_betas.
+    lmat_sqrt_betas: list = None
 
 
 def init_chain(hp: Hyper, ft: FourierTables, init_w_half: list, init_solve_w_half: list) -> ChainState:
@@ -422,18 +425,19 @@ def one_step(st: ChainState, ft: FourierTables, H, HtH, y, delta, noise: dict, t
     import time
     K = len(st.noise_cur)
     N, M = ft.N, H.shape[0]
+    lsb = st.sqrt_betas if st.lmat_sqrt_betas is None else st.lmat_sqrt_betas           # LMat.sqrt_beta (construct_from, 179)
     t0 = time.perf_counter()
     for k in range(K - 1):                                                               # 557
         st.noise_new[k] = st.betaZ * st.noise_cur[k] + st.beta * symmetrize(noise["w_half"][k])   # 558 -> 790
         if k == 0:
             st.u_new_sym[0] = st.stdev_sym * st.noise_new[0]                              # 563
         else:
-            st.L_latest[k] = assemble_L(st.u_new_sym[k - 1], st.sqrt_betas[k], ft)        # 560
+            st.L_latest[k] = assemble_L(st.u_new_sym[k - 1], lsb[k], ft)                  # 560
             st.u_new_sym[k] = np.linalg.solve(st.L_latest[k], st.noise_new[k])            # 561
     t1 = time.perf_counter()
     phi_cur = phi_woodbury(st.L_cur[K - 1], H, HtH, y, delta)                             # 567-568
     t2 = time.perf_counter()
-    st.L_latest[K - 1] = assemble_L(st.u_new_sym[K - 2], st.sqrt_betas[K - 1], ft)        # 570
+    st.L_latest[K - 1] = assemble_L(st.u_new_sym[K - 2], lsb[K - 1], ft)                  # 570
     t3 = time.perf_counter()
     phi_new = phi_woodbury(st.L_latest[K - 1], H, HtH, y, delta)                          # 571
     t4 = time.perf_counter()
@@ -471,6 +475,8 @@ def one_step_for_sqrt_betas(st: ChainState, ft: FourierTables, H, HtH, y, delta,
     (699-708) updates ``sqrt_beta``/``current_L``/``stdev_sym`` but NOT the current samples.
     noise: dict(z = n_layers normals, e = M normals, log_u)."""
     K, N = len(st.noise_cur), ft.N
+    if st.lmat_sqrt_betas is None:
+        st.lmat_sqrt_betas = list(lmat_sqrt_betas)       # from now on plain steps keep assembling with these (quirk, 179 vs 704)
     s = pcn_step_sqrt_betas
     sd = np.ones(K) if stdev_sqrt_betas is None else np.asarray(stdev_sqrt_betas)
     z = sd * noise["z"]                                                                            # 668

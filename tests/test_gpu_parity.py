@@ -757,6 +757,41 @@ def test_full_size_step_3m_vs_4m(full):
     assert float((v3 - v4).abs().max()) <= 1e-9 * float(v4.abs().max())
 
 
+def test_config2_full_size_chain_vs_oracle_golden(golden_dir, gemm_mode):
+    """BASELINE configs[1] (n=32, 90 angles, 3 layers) against the ORACLE itself: tests/golden/oracle_config2_n32.npz holds two
+    whole oracle iterations (oracle/make_golden.py --config2; ~35 s of CPU each, which is why they are precomputed).  Inputs
+    and the initial chain state are regenerated here by the same deterministic oracle calls (seconds); the CUDA step runs under
+    both complex product schemes.  Accept flags identical; Phi and all three half-samples within 1e-10 / 1e-9."""
+    from mspde.core import MspdeContext
+    g = np.load(os.path.join(golden_dir, "oracle_config2_n32.npz"))
+    hp = o.Hyper(n_layers=3, n=32, n_ext=64, n_theta=90, beta=float(g["beta"]))
+    pb = o.synthetic_problem(hp)
+    ft, H, HtH, y, delta = pb["ft"], pb["H"], pb["HtH"], pb["y"], pb["delta"]
+    assert np.allclose([y.sum(), np.abs(y).sum()], g["y_checksum"], rtol=1e-12) and abs(delta - float(g["delta"])) <= 1e-12 * delta
+    pt = o.prior_tables(hp, ft)
+    K, M = 3, H.shape[0]
+    ns = o.NoiseStream(int(g["seed"]), K, ft.n_ravel, M)
+    st = o.init_chain(hp, ft, [ns.half() for _ in range(K)], [ns.half() for _ in range(K)])
+    ctx = MspdeContext(32, 64, M, K)
+    ctx.set_inputs(H, HtH, y, ft.D_diag, pt["stdev_sym"], delta)
+    cb = _load_chain(ctx, st)
+    rec = torch.zeros((K, ft.n_ravel), dtype=torch.complex128, device=ctx.device)
+    for it in range(len(g["accepted"])):
+        nz = ns.draw_iteration()
+        assert abs(nz["log_u"] - float(g["log_u"][it])) < 1e-15
+        out = ctx.pcn_step(cb, [ctx.to_dev(w) for w in nz["w_half"]], nz["log_u"], ctx.to_dev(nz["w_last"]), ctx.to_dev(nz["e"]),
+                           record=rec).cpu().numpy()
+        ctx.check_info("step")
+        assert int(out[0]) == int(g["accepted"][it])
+        assert abs(out[2] - g["phi_cur"][it]) <= RTOL * abs(g["phi_cur"][it]), (it, out, g["phi_cur"][it])
+        assert abs(out[3] - g["phi_new"][it]) <= RTOL * abs(g["phi_new"][it]), (it, out, g["phi_new"][it])
+        assert abs(out[1] - g["log_ratio"][it]) <= RTOL * max(abs(g["phi_cur"][it]), abs(g["phi_new"][it]))
+        assert rel(rec.cpu(), g["halves"][it]) < 1e-9                   # solves amplify rounding by cond(L) ~ 1e4-1e5
+        for k in range(K):
+            assert rel(cb.u_new[k].cpu(), g["u_new"][it][k]) < 1e-9, (it, k)
+    ctx.close()
+
+
 def test_block_distributed_phi_matches_single_gpu(toy):
     """mspde.dist.DistPhi (block-cyclic row layout, panel broadcasts) in a 1-rank NCCL group, several panels (nb=64),
     against the single-GPU Phi.  The multi-rank equality and the n=96 run are in profiles/r01_dist_phi_*.log."""
