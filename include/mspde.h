@@ -35,6 +35,12 @@ long long mspde_launch_count(void);   /* kernels launched by the library so far 
 enum { MSPDE_GEMM_4M = 0, MSPDE_GEMM_3M = 1 };
 int mspde_set_gemm_mode(int mode);
 int mspde_get_gemm_mode(void);
+/* Experiment knob (default 0 = off; environment MSPDE_GEMM_PRE_MIN): under MSPDE_GEMM_3M, products with min(m, n) >= this
+ * threshold form the two T3 operand planes (Ar +- Ai, Br + Bi) once per operand in a separate pass and run the kernel variant
+ * that reads them instead of forming them per tile inside the main loop.  Same arithmetic, bit-identical results; measured
+ * 11-24 % SLOWER on B200 (extra L2 -> shared-memory traffic), see profiles/r02_gemm_pre_v1.log. */
+int mspde_set_gemm_pre_min(int min_mn);
+int mspde_get_gemm_pre_min(void);
 
 /* Context = sizes + borrowed fixed inputs + library-owned workspace (replaces the managed-memory pool and the
  * temporaries of pCN._log_ratio, mcmc/image_cupy.py:834-835, 634-643). */

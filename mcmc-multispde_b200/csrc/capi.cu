@@ -46,6 +46,8 @@ const char* mspde_last_error(void) { return get_error(); }
 long long mspde_launch_count(void) { return g_launches; }
 int mspde_set_gemm_mode(int mode) { return set_gemm_mode(mode); }
 int mspde_get_gemm_mode(void) { return gemm_mode(); }
+int mspde_set_gemm_pre_min(int v) { return set_gemm_pre_min(v); }
+int mspde_get_gemm_pre_min(void) { return gemm_pre_min(); }
 
 int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n_layers, void* stream) {
     return mspde_ctx_create_ex(out, device, n, n_ext, M, n_layers, stream, 0);

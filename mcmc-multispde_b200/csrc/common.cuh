@@ -77,6 +77,8 @@ enum { GEMM_FULL = 0, GEMM_UPPER = 1 };
 enum { GEMM_4M = 0, GEMM_3M = 1, GEMM_DEFAULT_MODE = GEMM_3M };
 int gemm_mode();
 int set_gemm_mode(int mode);
+int gemm_pre_min();
+int set_gemm_pre_min(int v);
 // C[i][j] = alpha * sum_k opA(A[k][i]) * B[k][j] + beta * C[i][j];  A: k x m, B: k x n, C: m x n, row-major.
 int zgemm_tn(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, const cplx* A, int lda,
              const cplx* B, int ldb, double beta, cplx* C, int ldc, int uplo);

