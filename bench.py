@@ -235,6 +235,122 @@ def library_standin_ms(sim, noise, reps=2):
     return best
 
 
+def config5_block(cfg, dev, rank, world, steps, warmup, fp64_peak, selfcheck_n=(32,), local_rank=0):
+    """BASELINE configs[4] as a sampler: one n=96 chain (N=36481, M=17190) stepped by mspde.dist.DistPCN with every dense piece
+    block-distributed over the ranks.  Returns the record (collective: every rank must call it)."""
+    import torch
+    import torch.distributed as dist
+    from mspde import _ffi
+    from mspde.dist import build_dist_chain
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import dist_chain_check as dcc
+    f_iter, N, M = flops_iter(**cfg)
+    out = {"config": {"workload": f"BASELINE configs[4]: 3 layers, n={cfg['n']} (N={N}, M={M}), single chain, every factorization "
+                                  "block-distributed over NCCL/NVLink (mspde.dist.DistPCN: state, injected noise, accept on the "
+                                  "all-reduced Phi values, Gibbs draw with both outcomes' right-hand sides)"}}
+    # (1) correctness evidence recorded with the number: distributed sampler == single-GPU kernels on the same inputs
+    out["selfcheck_vs_single_gpu"] = [dcc.single_vs_dist(n, dev, rank) for n in selfcheck_n]
+    torch.cuda.empty_cache()
+    # (2) the n=96 chain
+    t0 = time.perf_counter()
+    chain, noise_fn = build_dist_chain(cfg["n"], cfg["n_ext"], cfg["n_theta"], cfg["n_layers"], dev, seed=7, beta=0.3)
+    torch.cuda.synchronize()
+    out["setup_s"] = time.perf_counter() - t0
+
+    def timed_step():
+        nz = noise_fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = time.perf_counter()
+        d = chain.one_step(*nz)
+        torch.cuda.synchronize()
+        dist.barrier()
+        return time.perf_counter() - t, d
+    for _ in range(warmup):
+        timed_step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    runs = [timed_step() for _ in range(steps)]
+    out["clocks"] = sampler.stop()
+    tt = torch.tensor([sum(r[0] for r in runs)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    sec = float(tt.item()) / steps
+    out.update({"value": 1.0 / sec, "ms_per_step": 1e3 * sec, "gemm_scheme": "3m" if _ffi.get_gemm_mode() == _ffi.GEMM_3M else "4m",
+                "steps_detail": [dict(seconds=r[0], accepted=bool(r[1]["accepted"]), phi_cur=r[1]["phi_cur"], phi_new=r[1]["phi_new"])
+                                 for r in runs],
+                "finite": bool(all(np.isfinite(r[1]["phi_new"]) for r in runs) and torch.isfinite(chain.u_new[-1].abs()).all()),
+                "roofline": {"bound": "tensor", "achieved": f_iter / sec / 1e12 / world, "peak": fp64_peak, "unit": "TFLOP/s per GPU",
+                             "frac": f_iter / sec / 1e12 / world / fp64_peak, "aggregate_tflops": f_iter / sec / 1e12,
+                             "executed_frac": (0.75 if _ffi.get_gemm_mode() == _ffi.GEMM_3M else 1.0) * f_iter / sec / 1e12 / world / fp64_peak,
+                             "traffic": None}})
+    # (3) the collective that bounds a panel step: ncclBroadcast of the widest Cholesky panel (512 x N complex128)
+    pan = torch.zeros((512, N), dtype=torch.complex128, device=dev)
+    for _ in range(2):
+        dist.broadcast(torch.view_as_real(pan), src=0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        dist.broadcast(torch.view_as_real(pan), src=0)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_b = e0.elapsed_time(e1) / 5
+    out["panel_broadcast"] = {"what": "ncclBroadcast of one 512-row Cholesky panel (512 x N complex128), the largest message of a panel "
+                                      "step; hidden behind the K=512 trailing update by the one-panel look-ahead",
+                              "bytes": 512 * N * 16, "ms": ms_b, "GB_per_s": 512 * N * 16 / ms_b * 1e-6,
+                              "trailing_update_ms_at_peak": 0.75 * 4.0 * 512 * (N / world) * N / (fp64_peak * 1e12) * 1e3}
+    del pan, chain
+    torch.cuda.empty_cache()
+    return out
+
+
+def config4_block(cfg, dev, rank, world, local_rank, total_chains=64, steps_per_chain=2):
+    """BASELINE configs[3]: 64 independent chains sharded over the GPUs (chain c -> rank c mod G), stepped round-robin on each
+    GPU through one shared context (mspde.parallel.MultiChain), then ONE NCCL gather of the recorded samples and the pooled
+    acceptance / Welford field statistics.  Strong scaling: the 64-chain workload is fixed, the GPUs vary."""
+    import torch
+    import torch.distributed as dist
+    from mspde import image as im, parallel
+    K = cfg["n_layers"]
+    mine = parallel.shard_chains(total_chains, world, rank)
+    sim = im.Simulation(n_layers=K, n_samples=steps_per_chain + 2, n=cfg["n"], n_extended=cfg["n_ext"], beta=BENCH_BETA, kappa=5e9,
+                        sigma_0=4e7, sigma_v=3.2e4, sigma_scaling=0.4, meas_std=0.2, evaluation_interval=10, printProgress=False,
+                        seed=parallel.chain_seed(1, mine[0]), burn_percentage=25.0, enable_step_adaptation=True, pcn_variant="dunlop",
+                        phantom_name="shepp.png", meas_type="tomo", n_theta=cfg["n_theta"], verbose=False, device=local_rank)
+    sim.pcn.set_chol_epsilon(1e-6)
+    mc = parallel.MultiChain(sim, mine, base_seed=1, accumulate_stats=True)
+    for ch in mc.chains:
+        make_state_consistent(ch["Layers"])
+    mc.step_all()                                   # one warm-up iteration of every chain
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps_per_chain):
+        mc.step_all()
+    hist = torch.as_tensor(mc.histories()).to(dev)                           # [local chains, K, rows, n_ravel]
+    full = parallel.gather_samples(hist, total_chains, world)               # the final NCCL gather (configs[3])
+    stats = mc.pooled_field_statistics()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    a, n = mc.accepted_and_steps()
+    acc = parallel.pooled_acceptance(a, n)
+    sim.pcn.ctx.check_info("config 4 chains")
+    ms = float(t.item())
+    out = {"workload": f"BASELINE configs[3]: {total_chains} independent chains, {K} layers, n={cfg['n']}, sharded c mod G over {world} GPUs, "
+                       "final NCCL gather of samples + pooled acceptance and Welford field statistics inside the timed region",
+           "chains": total_chains, "chains_per_gpu": len(mine), "steps_per_chain": steps_per_chain, "scaling": "strong",
+           "value": total_chains * steps_per_chain / (ms * 1e-3), "unit": "iters/s", "ms_total": ms,
+           "gathered_shape": list(full.shape), "pooled_acceptance": acc, "pooled_stats_count": int(stats[0]["count"]),
+           "pooled_u_mean_abs_max": float(stats[-1]["u_mean"].abs().max())}
+    sim.pcn.ctx.close()
+    del mc, sim, hist, full
+    torch.cuda.empty_cache()
+    return out
+
+
 def make_state_consistent(Layers):
     """Bench setup only.  Simulation.__init__ leaves every layer's current sample and current noise from DIFFERENT draws
     (image_cupy.py:735 vs 755), so until a first acceptance every proposal -- built from the noise -- is a jump
@@ -289,6 +405,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the separately-reported results-preserving formulations")
     ap.add_argument("--gemm", default=None, choices=["3m", "4m"],
                     help="complex product scheme of the GEMM kernel for the headline (default: the library's, 3m)")
+    ap.add_argument("--with-config5", action="store_true", help="also run the n=96 block-distributed chain at fewer than 8 GPUs")
     ap.add_argument("--beta", type=float, default=None, help="pCN step size of the bench chains (default BENCH_BETA)")
     ap.add_argument("--chains-per-gpu", type=int, default=1,
                     help="config 4 (many independent chains): also report the throughput with this many chains in flight per GPU")
@@ -319,34 +436,18 @@ def main():
     FP64_PEAK_TFLOPS, fp64_peak_source = measure_fp64_peak(_ffi)
     if args.config == 5:
         # BASELINE configs[4]: a single n=96 chain whose dense work is block-distributed over the GPUs (strong scaling)
-        from mspde.dist import DistStep
         if world < 2:
             raise SystemExit("config 5 (n=96) needs at least 2 GPUs: python -m torch.distributed.run ... bench.py --config 5")
         if args.gemm is not None:
             _ffi.set_gemm_mode(_ffi.GEMM_3M if args.gemm == "3m" else _ffi.GEMM_4M)
-        stp = DistStep(cfg["n"], cfg["n_ext"], cfg["n_theta"], dev)
-        for _ in range(min(args.warmup, 1)):
-            stp.run_overlapped()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        runs = [stp.run_overlapped() for _ in range(args.steps)]
-        clocks = sampler.stop()
-        stp.verify = True                      # one extra, untimed iteration with residual checks
-        checks = stp.run_overlapped()["checks"]
-        sec = sum(r["seconds"] for r in runs) / len(runs)
+        blk = config5_block(cfg, dev, rank, world, steps=args.steps, warmup=min(args.warmup, 1), fp64_peak=FP64_PEAK_TFLOPS,
+                            selfcheck_n=(32,), local_rank=local_rank)
         if rank == 0:
-            emit({"metric": "pCN iters/sec (n=96, 3 layers, one chain block-distributed)", "value": 1.0 / sec,
-                              "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1),
-                              "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                              "dtype": "f64", "data": "synthetic",
-                              "config": {"workload": "BASELINE configs[4]: 3 layers, n=96 (N=36481, M=17190), single chain, dense "
-                                                     "solves block-distributed over NCCL/NVLink", "pieces_s": runs[-1]["pieces_s"]},
-                              "roofline": {"bound": "tensor", "achieved": f_iter / sec / 1e12 / world, "peak": FP64_PEAK_TFLOPS,
-                                           "unit": "TFLOP/s per GPU", "frac": f_iter / sec / 1e12 / world / FP64_PEAK_TFLOPS,
-                                           "aggregate_tflops": f_iter / sec / 1e12, "traffic": None},
-                              "gemm_scheme": "3m" if _ffi.get_gemm_mode() == _ffi.GEMM_3M else "4m",
-                              "clocks": clocks, "finite": all(r["finite"] for r in runs), "residual_checks": checks,
-                              "phi_latest": runs[-1]["phi"]})
+            line = {"metric": "pCN iters/sec (n=96, 3 layers, one chain block-distributed)", "value": blk["value"], "unit": "iters/s",
+                    "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": blk["ms_per_step"],
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+            line.update({k: v for k, v in blk.items() if k not in ("value", "ms_per_step")})
+            emit(line)
         dist.destroy_process_group()
         return
     K = cfg["n_layers"]
@@ -617,6 +718,23 @@ def main():
         rate, desc, cores, dt, done = cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=30.0)
         cpu_baseline = {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": desc}
 
+    config4 = config5 = None
+    if world > 1 and args.config == 2 and not args.no_extras:
+        # the two multi-GPU splits north_star names, measured in the same driver-visible run
+        sim.pcn.ctx.close()
+        del sim, pcn, ctx, Layers, cb, dev_noise, rec, outs
+        torch.cuda.empty_cache()
+        try:
+            config4 = config4_block(cfg, dev, rank, world, local_rank)
+        except Exception as ex:                     # keep the headline line even if an extra block fails
+            config4 = {"unavailable": repr(ex)[:300]}
+        if world >= 8 or args.with_config5:
+            try:
+                config5 = config5_block(CONFIGS[5], dev, rank, world, steps=2, warmup=1, fp64_peak=FP64_PEAK_TFLOPS,
+                                        selfcheck_n=(32,), local_rank=local_rank)
+            except Exception as ex:
+                config5 = {"unavailable": repr(ex)[:300]}
+
     if rank == 0:
         line = {"metric": f"pCN iters/sec (n={cfg['n']}, {cfg['n_layers']} layers)", "value": value, "unit": "iters/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -624,7 +742,7 @@ def main():
                 "config": workload_config(cfg, world),
                 "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "library_standin": library,
+                "library_standin": library, "config4_64_chains": config4, "config5_n96_distributed": config5,
                 "gemm_scheme": "3m" if gemm_mode == _ffi.GEMM_3M else "4m", "acceptance_rate": acc_rate, "setup_s": t_setup}
         line.update(extra)
         emit(line)
