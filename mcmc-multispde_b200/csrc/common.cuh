@@ -70,6 +70,19 @@ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
     return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: a process that opens contexts on several GPUs has to repeat
+// it on each.  DeviceOnce::first() is true the first time it is asked on the current device.
+struct DeviceOnce {
+    bool seen[64] = {};
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+        if (seen[d]) return false;
+        seen[d] = true;
+        return true;
+    }
+};
+
 // ---- GEMM (zgemm_tn.cu) --------------------------------------------------------------------------
 enum { GEMM_FULL = 0, GEMM_UPPER = 1 };
 // Complex product scheme of every GEMM launch: 4M = four real products (8 flop per complex multiply-add), 3M = three real

@@ -325,7 +325,7 @@ QrWork carve(void* work, int rows, int cols) {
     return w;
 }
 
-bool g_attr = false;
+DeviceOnce g_attr;
 
 }  // namespace
 
@@ -346,11 +346,10 @@ size_t qr_work_bytes(int rows, int cols) {
 // Householder QR of the leading `cols` columns of Aaug (rows x (cols + naug)), trailing columns get Q^H applied.
 // logabs (device, optional) accumulates sum log |r_jj|.
 static int init_attrs() {
-    if (!g_attr) {
+    if (g_attr.first()) {
         MSPDE_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MSPDE_CUDA(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(cplx) * PW * (PW + 1))));
         MSPDE_CUDA(cudaFuncSetAttribute(trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
-        g_attr = true;
     }
     return 0;
 }

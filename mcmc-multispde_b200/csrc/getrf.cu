@@ -271,7 +271,7 @@ LuWork carve(void* work, int n, int ntot) {
     return w;
 }
 
-bool g_attr = false;
+DeviceOnce g_attr;
 
 }  // namespace
 
@@ -288,9 +288,8 @@ size_t lu_work_bytes(int n, int ntot) {
 // carve(work, n, ntot)) receives L^T, (L11^-1)^T and the net row permutation of the panel.
 int lu_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int goff, int n, int ntot, void* work, int* info,
                     double* logabs) {
-    if (!g_attr) {
+    if (g_attr.first()) {
         MSPDE_CUDA(cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        g_attr = true;
     }
     LuWork w = carve(work, n, ntot);
     int G = min(MAXG, (mp + 63) / 64);

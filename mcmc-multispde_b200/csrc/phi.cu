@@ -26,31 +26,8 @@ __global__ void add_diag_kernel(cplx* __restrict__ A, int lda, int n, double v) 
     if (i < n) A[size_t(i) * lda + i].x += v;
 }
 
-// one warp per row j of the upper factor V: z_j = sum_{i>=j} V[j][i] y_i ; rowsq[j] = |z_j|^2 ; rowlog[j] = log V[j][j]
-__global__ void __launch_bounds__(256) vy_kernel(const cplx* __restrict__ V, int ldv, const double* __restrict__ y, int M,
-                                                 double* __restrict__ rowsq, double* __restrict__ rowlog) {
-    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (j >= M) return;
-    const cplx* row = V + size_t(j) * ldv;
-    double sx = 0.0, sy = 0.0;
-    for (int i = j + lane; i < M; i += 32) {
-        const cplx v = row[i];
-        const double yi = y[i];
-        sx = fma(v.x, yi, sx);
-        sy = fma(v.y, yi, sy);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o);
-        sy += __shfl_xor_sync(0xffffffffu, sy, o);
-    }
-    if (lane == 0) {
-        rowsq[j] = sx * sx + sy * sy;
-        rowlog[j] = log(row[j].x);
-    }
-}
-
+// one warp per row j of an upper-trapezoidal row panel V (nrows x ncols, diagonal at column 0 of row 0):
+// z_j = sum_{i>=j} V[j][i] y_i ; rowsq[j] = |z_j|^2 ; rowlog[j] = log Re V[j][j]   (image_cupy.py:643)
 __global__ void __launch_bounds__(256) vy_rows_kernel(const cplx* __restrict__ V, int ldv, const double* __restrict__ y,
                                                       int nrows, int ncols, double* __restrict__ rowsq,
                                                       double* __restrict__ rowlog) {
@@ -286,7 +263,7 @@ int phi_eval(Ctx* c, cudaStream_t st, PhiWork& w, const cplx* L, int ldl, double
     MSPDE_LAUNCH_CHECK();
     rc = potrf_upper(st, w.Q, c->ldM, M, w.winv, c->info, serial ? nullptr : &w.la);
     if (rc) return rc;
-    vy_kernel<<<(M + 7) / 8, 256, 0, st>>>(w.Q, c->ldM, c->y, M, w.rowsq, w.rowlog);
+    vy_rows_kernel<<<(M + 7) / 8, 256, 0, st>>>(w.Q, c->ldM, c->y, M, M, w.rowsq, w.rowlog);
     MSPDE_LAUNCH_CHECK();
     phi_reduce_kernel<<<1, 1024, 0, st>>>(w.rowsq, w.rowlog, M, out3);
     MSPDE_LAUNCH_CHECK();

@@ -37,7 +37,6 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(cplx* __restrict__ A, i
             if (i >= nb && i == j) v = make_double2(1.0, 0.0);   // identity padding for edge blocks
             r[a][b] = v;
         }
-    bool bad = false;
     for (int k = 0; k < NB; ++k) {
         const int ka = k >> 4, kr = k & 15;
         if (ty == kr) {
@@ -51,8 +50,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(cplx* __restrict__ A, i
         __syncthreads();
         const double akk = rowbuf[k & 1][k].x;
         if (!(akk > 0.0)) {
-            bad = true;   // not positive definite (or NaN): LAPACK zpotrf info = k+1
-            if (tid == 0) atomicCAS(info, 0, goff + k + 1);
+            if (tid == 0) atomicCAS(info, 0, goff + k + 1);   // not positive definite (or NaN): LAPACK zpotrf info = k+1
         }
         const double inv = rsqrt(akk);
         const double d = akk * inv;
@@ -76,7 +74,6 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(cplx* __restrict__ A, i
             }
         }
     }
-    (void)bad;
     // publish U to shared memory and to A (upper triangle only)
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -122,7 +119,7 @@ int split(int n) {
     return n1;
 }
 
-bool g_attr = false;
+DeviceOnce g_attr;
 
 }  // namespace
 
@@ -143,24 +140,6 @@ int trsm_uh(cudaStream_t st, const cplx* U, int ldu, const cplx* winv, int n, cp
                    ldb, ncols);
 }
 
-static int potrf_rec(cudaStream_t st, cplx* A, int lda, int n, int goff, cplx* winv, int* info) {
-    if (n <= NB) {
-        potrf_diag_kernel<<<1, 256, NB * SP * sizeof(cplx), st>>>(A, lda, n, goff, winv, info);
-        MSPDE_LAUNCH_CHECK();
-        return 0;
-    }
-    const int n1 = split(n);
-    int rc = potrf_rec(st, A, lda, n1, goff, winv, info);
-    if (rc) return rc;
-    cplx* A12 = A + n1;
-    cplx* A22 = A + size_t(n1) * lda + n1;
-    rc = trsm_uh(st, A, lda, winv, n1, A12, lda, n - n1);          // U12 = U11^-H A12
-    if (rc) return rc;
-    rc = zgemm_tn(st, true, n - n1, n - n1, n1, -1.0, A12, lda, A12, lda, 1.0, A22, lda, GEMM_UPPER);  // A22 -= U12^H U12
-    if (rc) return rc;
-    return potrf_rec(st, A22, lda, n - n1, goff + n1, winv + size_t(n1 / NB) * NB * NB, info);
-}
-
 // In-place upper Cholesky of the Hermitian matrix whose upper triangle is stored in A (row-major).
 // winv must hold ceil(n/64) * 64*64 complex.  *info (device) receives the first failing column (1-based), 0 if ok.
 //
@@ -169,10 +148,9 @@ static int potrf_rec(cudaStream_t st, cplx* A, int lda, int n, int goff, cplx* w
 // of panel p is split: the block row of panel p+1 is updated on the main stream, the rest on an auxiliary
 // (lower-priority) stream, so that the latency-bound factorisation of panel p+1 runs underneath the big HERK.
 int potrf_upper(cudaStream_t st, cplx* A, int lda, int n, cplx* winv, int* info, const LookAhead* la) {
-    if (!g_attr) {
+    if (g_attr.first()) {
         MSPDE_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(NB * SP * sizeof(cplx))));
-        g_attr = true;
     }
     static const int NBO = getenv("MSPDE_POTRF_NBO") ? atoi(getenv("MSPDE_POTRF_NBO")) : 512;   // outer panel width (multiple of 64)
     const bool ahead = la && la->aux && n > 2 * NBO;

@@ -76,7 +76,7 @@ int split(int n) {
     return n1;
 }
 
-bool g_attr = false;
+DeviceOnce g_attr;
 
 int trsm_rec(cudaStream_t st, const cplx* Ut, int ldut, const cplx* invT, int n, cplx* B, int ldb, int ncols) {
     if (n <= NB)   // X = U_ii^-1 B in place (single row tile)
@@ -103,9 +103,8 @@ int transpose(cudaStream_t st, const cplx* in, int ldi, int rows, int cols, bool
 // B (n x ncols) <- U^-1 B for the upper triangle U of a row-major matrix.  Ut (n x n, ldut) and invT (ceil(n/64) blocks of
 // 64 x 64) are workspace.
 int trsm_upper(cudaStream_t st, const cplx* U, int ldu, int n, cplx* B, int ldb, int ncols, cplx* Ut, int ldut, cplx* invT) {
-    if (!g_attr) {
+    if (g_attr.first()) {
         MSPDE_CUDA(cudaFuncSetAttribute(triu_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * SP * sizeof(cplx))));
-        g_attr = true;
     }
     int rc = transpose(st, U, ldu, n, n, false, Ut, ldut);
     if (rc) return rc;

@@ -5,10 +5,19 @@
 // A is K x m, B is K x n, C is m x n, all row-major interleaved complex128.  This single "TN" form is
 // what every dense step of the pCN path reduces to (L^H L, U12^H U12 trailing updates, U^-H B solves,
 // V^H A block reflectors): both operands are read along contiguous rows, so tiles are fetched with
-// 1-D TMA bulk copies (cp.async.bulk.shared::cluster.global, one row segment per copy, mbarrier
-// complete_tx) into padded, bank-conflict-free shared-memory rows.
+// 1-D bulk copies (cp.async.bulk.shared::cluster.global -- the non-tensor form of the TMA unit, SASS UBLKCP: one row
+// segment per copy, no tensor map, so it works on arbitrary sub-blocks; completion by mbarrier complete_tx) into padded,
+// bank-conflict-free shared-memory rows.
 //
-// Complex arithmetic stays 4M (no Gauss/3M trick): a complex m x n x k product is run as the real
+// Two kernels, one per complex product scheme (mspde_set_gemm_mode / MSPDE_GEMM=3m|4m; DEFAULT: 3M, common.cuh):
+//   zgemm3m_tn_kernel  three real DMMA products per complex product (6 flop per complex multiply-add), further down;
+//   zgemm_tn_kernel    four real products (8 flop), directly below.
+// Accuracy trade-off of the default: 3M keeps the normwise bound O(u) sum |a||b| of 4M but loses the componentwise bound on
+// the imaginary part (Higham, Accuracy and Stability, 23.2.4), and the beta != 0 preload forms Im(s c) as s(cr + ci) - s cr,
+// which cancels when |cr| >> |ci|.  No consumer on the path relies on the componentwise bound (Cholesky leaves read only the
+// real part of the diagonal); the parity tests run under BOTH schemes at 1e-10 and bench.py reports both rates.
+//
+// 4M: a complex m x n x k product is run as the real
 // product  C(m x 2n) = A(m x 2k) * B~(2k x 2n)  where A is used as stored (interleaved re/im along k)
 // and B~ is the real 2x2 expansion [[br, bi], [-bi, br]] of B.  The expansion is never materialised: a
 // lane of the k4 x n8 "col" fragment picks its component ((k'&1)^(n'&1)) and sign ((k'&1)&!(n'&1)) when
@@ -235,12 +244,12 @@ __global__ void __launch_bounds__(THREADS, 2) zgemm_tn_kernel(GemmArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// 3M variant (opt-in, MSPDE_GEMM_3M=1): three real products per complex product instead of four,
+// 3M variant (the default scheme, common.cuh: GEMM_DEFAULT_MODE): three real products per complex product instead of four,
 //     T1 = Ar^T Br,  T2 = Ai^T Bi,  T3 = (Ar +- Ai)^T (Br + Bi)
 //     plain: C = (T1 - T2) + i (T3 - T1 - T2)        conj(A): C = (T1 + T2) + i (T3 - T1 + T2)   [T3 built with Ar - Ai]
 // so the FP64 tensor pipe executes 6 instead of 8 real flops per complex multiply-add (cuBLAS calls the same scheme
 // ZGEMM3M).  Normwise the rounding error stays O(u) * sum |a||b|; the imaginary part loses the componentwise bound of the
-// 4M form, which is why this is an option measured beside the default and not the default itself.
+// 4M form (see the header of this file), which is why the 4M kernel stays selectable and is measured beside it.
 // One DMMA.8x8x4 is a real 8 x 8 x 4 product here: a lane loads one complex A element (k = t, row g) and one complex B
 // element (k = t, col g) with a 128-bit shared-memory load and feeds re, im and re+-im to the three accumulator sets.
 // Three accumulator sets cost 1.5x the registers, so the CTA tile is 64 x 32 (8 MMA warps of 16 x 16), still 2 CTAs/SM.
@@ -739,17 +748,16 @@ __global__ void splitk_reduce_kernel(const cplx* __restrict__ part, int nsplit, 
     *c = out;
 }
 
-bool g_attr_set = false;
+DeviceOnce g_attr_set;
 
 int launch(cudaStream_t st, const GemmArgs& a, int nz) {
     if (a.m <= 0 || a.n <= 0) return 0;
     const bool use3m = gemm_mode() == GEMM_3M;
-    if (!g_attr_set) {
+    if (g_attr_set.first()) {
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm3m_tn_kernel<M3N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3N::SMEM_BYTES));
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm3m_tn_kernel<M3T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3T::SMEM_BYTES));
         MSPDE_CUDA(cudaFuncSetAttribute(zgemm3m_pre_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3P::SMEM_BYTES));
-        g_attr_set = true;
     }
     static FILE* logf = getenv("MSPDE_GEMM_LOG") ? fopen(getenv("MSPDE_GEMM_LOG"), "w") : nullptr;   // dev aid: shapes per launch
     if (logf) { fprintf(logf, "%d %d %d %d %d\n", a.m, a.n, a.k, a.uplo, nz); fflush(logf); }

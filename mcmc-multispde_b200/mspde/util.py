@@ -67,10 +67,11 @@ def w_half_from_normals(re, im):
 
 
 def printProgressBar(iteration, total, prefix="", suffix="", decimals=1, length=100, fill="#"):
-    """util.printProgressBar (mcmc/util_cupy.py:139-157)."""
-    percent = ("{0:." + str(decimals) + "f}").format(100 * (iteration / float(total)))
-    filled = int(length * iteration // total)
-    bar = fill * filled + "-" * (length - filled)
-    print("\r%s |%s| %s%% %s" % (prefix, bar, percent, suffix), end="\r")
-    if iteration == total:
-        print()
+    """Same call signature as the reference's progress printer (mcmc/util_cupy.py:139-157); one carriage-return-refreshed line."""
+    import sys
+    frac = 0.0 if total <= 0 else min(1.0, max(0.0, iteration / float(total)))
+    done = int(round(length * frac))
+    sys.stdout.write("\r{} [{}{}] {:.{d}f}% {}".format(prefix, fill * done, "." * (length - done), 100.0 * frac, suffix, d=decimals))
+    if iteration >= total:
+        sys.stdout.write("\n")
+    sys.stdout.flush()

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Driver with the flag surface of /root/reference/twoDsim.py (argparse block 68-97) on top of mspde.image.
 
-Not carried over (out of the hot-path scope): FBP initialisation through skimage.iradon, HDF5 chain
-continuation, Slurm self-resubmission and post_analysis plotting.  `--chains` / torchrun adds the chain-parallel mode."""
+FBP initialisation (seq-no 0) and chain continuation from the previous sequence's result file (seq-no > 0) follow
+twoDsim.py:133-136 through mspde.io.  Not carried over (out of the hot-path scope): Slurm self-resubmission and
+post_analysis plotting."""
 import argparse
 import datetime
 import os
@@ -11,20 +12,30 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-from mspde import image as im      # noqa: E402
+from mspde import image as im, io      # noqa: E402
 
 
-def _str_to_bool(s):
-    if s.lower() not in ['true', 'false']:
-        raise ValueError('Need bool; got %r' % s)
-    return {'true': True, 'false': False}[s.lower()]
+class _TriStateFlag(argparse.Action):
+    """Boolean option in the reference CLI's convention (twoDsim.py:91-96): ``--flag`` and ``--flag true|false`` set it,
+    ``--noflag`` clears it.  One action object serves both spellings."""
+
+    def __init__(self, option_strings, dest, default=False, help=None):
+        super().__init__(option_strings, dest, nargs="?", default=default, help=help)
+
+    def __call__(self, parser, namespace, values, option_string=None):
+        if option_string.startswith("--no"):
+            if values is not None:
+                parser.error(f"{option_string} takes no value")
+            setattr(namespace, self.dest, False)
+            return
+        text = "true" if values is None else str(values).strip().lower()
+        if text not in ("true", "false"):
+            parser.error(f"{option_string} expects true or false, got {values!r}")
+        setattr(namespace, self.dest, text == "true")
 
 
 def add_boolean_argument(parser, name, default=False, messages=""):
-    """parser_help.add_boolean_argument (/root/reference/parser_help.py:7-11)."""
-    group = parser.add_mutually_exclusive_group()
-    group.add_argument('--' + name, nargs='?', default=default, const=True, type=_str_to_bool, help=messages)
-    group.add_argument('--no' + name, dest=name, action='store_false', help=messages)
+    parser.add_argument("--" + name, "--no" + name, dest=name.replace("-", "_"), action=_TriStateFlag, default=default, help=messages)
 
 
 def main(argv=None):
@@ -75,8 +86,17 @@ def main(argv=None):
     parent = pathlib.Path(args.result_dir) if args.result_dir else pathlib.Path.cwd() / 'SimulationResult'
     folder = parent / ('result-' + datetime.datetime.now().strftime('%d-%b-%Y_%H_%M_%S') if args.seq_no == 0 else args.init_folder)
     folder.mkdir(parents=True, exist_ok=True)
+    rank_tag = os.environ.get("RANK", "0")
+    if args.seq_no == 0:                                         # twoDsim.py:133-136
+        io.initialize_using_FBP(sim)
+    else:
+        prev = folder / 'result_{}_rank{}.npz'.format(args.seq_no - 1, rank_tag)
+        if prev.exists():
+            io.initialize_from_file(sim, str(prev))              # initialize_from_folder, 36-54
+        else:
+            io.initialize_using_FBP(sim)                         # the reference's fallback when the file is missing (43-44)
     sim.run()
-    out = folder / 'result_{}_rank{}.npz'.format(args.seq_no, os.environ.get("RANK", "0"))
+    out = folder / 'result_{}_rank{}.npz'.format(args.seq_no, rank_tag)
     sim.save(str(out))
     print('simulation result stored in {} ({:.2f} it/s, acceptance {:.1%})'.format(
         out, args.n_samples / max(sim.total_time, 1e-9), sim.acceptancePercentage))

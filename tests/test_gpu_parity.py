@@ -914,3 +914,28 @@ def test_config3_size_phi_solve_and_lstsq():
     scale = (float(torch.linalg.norm(ctx.H)) ** 2 + float(torch.linalg.norm(Lc)) ** 2) * float(torch.linalg.norm(v))
     assert float(torch.linalg.norm(grad)) <= 1e-11 * scale
     ctx.close()
+
+
+def test_presummed_3m_kernel_is_bit_identical(lib):
+    """The experiment knob mspde_set_gemm_pre_min (pre-summed T3 operand planes, measured slower and off by default) performs
+    the same arithmetic as the in-loop sums: identical bits on edge shapes (odd sizes, k tails, beta != 0, upper, split-K)."""
+    from mspde import _ffi
+    mode0, pre0 = _ffi.get_gemm_mode(), _ffi.get_gemm_pre_min()
+    try:
+        _ffi.set_gemm_mode(_ffi.GEMM_3M)
+        for (m, n, k, conj, uplo, beta) in [(65, 33, 17, 1, 0, 0.0), (127, 63, 35, 0, 0, 1.0), (333, 333, 211, 1, 1, 1.0),
+                                            (200, 1031, 129, 1, 0, -0.5), (1, 1, 1, 1, 0, 0.0), (961, 961, 961, 1, 1, 0.0)]:
+            A = crandn(k, m, seed=1)
+            B = A if uplo else crandn(k, n, seed=2)
+            C0 = crandn(m, n, seed=3)
+            outs = []
+            for pre in (0, 1):
+                _ffi.set_gemm_pre_min(pre)
+                C = C0.clone()
+                _gemm(lib, A, B, C, bool(conj), 0.75, beta, uplo)
+                torch.cuda.synchronize()
+                outs.append(C)
+            assert torch.equal(outs[0], outs[1]), (m, n, k)
+    finally:
+        _ffi.set_gemm_mode(mode0)
+        _ffi.set_gemm_pre_min(pre0)
