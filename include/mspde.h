@@ -35,6 +35,12 @@ long long mspde_launch_count(void);   /* kernels launched by the library so far 
 enum { MSPDE_GEMM_4M = 0, MSPDE_GEMM_3M = 1 };
 int mspde_set_gemm_mode(int mode);
 int mspde_get_gemm_mode(void);
+/* Width of the block reflectors of the Householder QR behind util.lstsq (mcmc/util_cupy.py:590-609): 128 (default) applies two
+ * consecutive 64-column panels in one rank-128 trailing update, 64 applies every panel on its own (the round-1 path, kept for
+ * comparison; also what the block-distributed driver uses).  Same panel kernel, results agree to rounding.  Process-wide;
+ * environment MSPDE_QR_BLOCK=64|128. */
+int mspde_set_qr_block(int width);
+int mspde_get_qr_block(void);
 /* Experiment knob (default 0 = off; environment MSPDE_GEMM_PRE_MIN): under MSPDE_GEMM_3M, products with min(m, n) >= this
  * threshold form the two T3 operand planes (Ar +- Ai, Br + Bi) once per operand in a separate pass and run the kernel variant
  * that reads them instead of forming them per tile inside the main loop.  Same arithmetic, bit-identical results; measured

@@ -46,6 +46,8 @@ const char* mspde_last_error(void) { return get_error(); }
 long long mspde_launch_count(void) { return g_launches; }
 int mspde_set_gemm_mode(int mode) { return set_gemm_mode(mode); }
 int mspde_get_gemm_mode(void) { return gemm_mode(); }
+int mspde_set_qr_block(int k) { return set_qr_block_width(k); }
+int mspde_get_qr_block(void) { return qr_block_width(); }
 int mspde_set_gemm_pre_min(int v) { return set_gemm_pre_min(v); }
 int mspde_get_gemm_pre_min(void) { return gemm_pre_min(); }
 
@@ -136,6 +138,13 @@ int mspde_ctx_create_ex(mspde_ctx** out, int device, int n, int n_ext, int M, in
         if (dmalloc(&wq, qr_work_bytes(M + N, N))) { mspde_ctx_destroy(h); return -1; }
         h->owned.push_back(wq);
         c.qr_la.work2 = wq;
+        for (int q = 0; q < 2; ++q) {         // pair workspaces of the K = 128 block-reflector path of the Householder QR
+            unsigned char* wp = nullptr;
+            if (dmalloc(&wp, qr_pair_work_bytes(M + N, N, 2))) { mspde_ctx_destroy(h); return -1; }
+            h->owned.push_back(wp);
+            c.qr_la.pair[q] = wp;
+        }
+        c.qr_la.pair_rows = M + N; c.qr_la.pair_cols = N; c.qr_la.pair_naug = 2;
         int lo = 0, hi = 0;
         MSPDE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         MSPDE_CUDA(cudaStreamCreateWithPriority(&c.qr_la.aux, cudaStreamNonBlocking, g_qr_aux_prio));   // panel kernels: latency-critical

@@ -75,7 +75,7 @@ __device__ __forceinline__ cplx ldcg(const cplx* p) { return __ldcg(p); }
 
 // Panel: A[c0 + (0..mp-1)][c0 + (0..pw-1)], pw <= PW pivot columns.
 __global__ void __launch_bounds__(256) qr_panel_kernel(cplx* __restrict__ A, int lda, int mp, int pw, int slab,
-                                                       cplx* __restrict__ V, cplx* __restrict__ Vt, int ldvt,
+                                                       cplx* __restrict__ V, int ldv, cplx* __restrict__ Vt, int ldvt,
                                                        cplx* __restrict__ tau_out, cplx* dots, cplx* currow,
                                                        double* __restrict__ logabs, unsigned* barrier_counter,
                                                        cplx* gslab) {
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) qr_panel_kernel(cplx* __restrict__ A, int
             if (gi > j) e = v;
             else if (gi == j) e = make_double2(1.0, 0.0);
         }
-        V[size_t(gi) * PW + j] = e;
+        V[size_t(gi) * ldv + j] = e;
     }
     for (int idx = tid; idx < nrow * PW; idx += 256) {
         const int j = idx / nrow, i = idx % nrow;
@@ -356,9 +356,9 @@ static int init_attrs() {
 
 // Factor one 64-column panel Ap (mp rows x pw pivot columns, leading dimension lda): R and the reflectors in place, and in
 // the workspace (laid out by carve(work, rows, cols)) the explicit V (mp x 64), V^T (64 x ldvt) and the compact-WY T.
-int qr_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int rows, int cols, void* work, double* logabs) {
-    if (init_attrs()) return -1;
-    QrWork w = carve(work, rows, cols);
+// Launch of the cooperative panel kernel: R and the reflectors in place in Ap, explicit V (leading dimension ldv) and V^T.
+static int launch_panel(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, cplx* V, int ldv, cplx* Vt, int ldvt, cplx* tau,
+                        cplx* dots, cplx* currow, unsigned* bar, cplx* gslab_buf, double* logabs) {
     int G = min(MAXG, (mp + 63) / 64);
     int slab = (mp + G - 1) / G;
     G = (mp + slab - 1) / slab;
@@ -366,21 +366,27 @@ int qr_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int rows
     cplx* gslab = nullptr;
     static const bool force_global = getenv("MSPDE_FORCE_GSLAB") != nullptr;   // test hook for the tall-panel path
     if (force_global || smem > SMEM_SLAB_LIMIT) {   // tall panel: slabs live in the L2-resident scratch instead
-        gslab = w.gslab;
+        gslab = gslab_buf;
         smem = 0;
     }
-    cplx* V = w.V; cplx* Vt = w.Vt; int ldvt = w.ldvt; cplx* tau = w.tau; cplx* dots = w.dots; cplx* currow = w.currow;
-    int mp_ = mp, pw_ = pw, slab_ = slab, lda_ = lda;
+    int mp_ = mp, pw_ = pw, slab_ = slab, lda_ = lda, ldv_ = ldv, ldvt_ = ldvt;
     double* la = logabs;
-    unsigned* bar = w.bar;
     MSPDE_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
-    void* args[] = {&Ap, &lda_, &mp_, &pw_, &slab_, &V, &Vt, &ldvt, &tau, &dots, &currow, &la, &bar, &gslab};
+    void* args[] = {&Ap, &lda_, &mp_, &pw_, &slab_, &V, &ldv_, &Vt, &ldvt_, &tau, &dots, &currow, &la, &bar, &gslab};
     MSPDE_CUDA(cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3(G), dim3(256), args, smem, st));
     ++g_launches;
+    return 0;
+}
+
+int qr_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int rows, int cols, void* work, double* logabs) {
+    if (init_attrs()) return -1;
+    QrWork w = carve(work, rows, cols);
+    int rc = launch_panel(st, Ap, lda, mp, pw, w.V, PW, w.Vt, w.ldvt, w.tau, w.dots, w.currow, w.bar, w.gslab, logabs);
+    if (rc) return rc;
     // T from V^H V
     int ns_g = (mp + 127) / 128;
     if (ns_g > w.nsplit) ns_g = w.nsplit;
-    int rc = zgemm_tn_splitk(st, true, PW, PW, mp, 1.0, w.V, PW, w.V, PW, 0.0, w.Gm, PW, w.part, ns_g);
+    rc = zgemm_tn_splitk(st, true, PW, PW, mp, 1.0, w.V, PW, w.V, PW, 0.0, w.Gm, PW, w.part, ns_g);
     if (rc) return rc;
     larft_kernel<<<1, 256, 2 * sizeof(cplx) * PW * (PW + 1), st>>>(w.Gm, w.tau, pw, w.T);
     MSPDE_LAUNCH_CHECK();
@@ -414,12 +420,209 @@ void qr_work_layout(int rows, int cols, void* work, long long* out6) {
     out6[4] = reinterpret_cast<unsigned char*>(w.T) - base;   out6[5] = (long long)PW * PW * sizeof(cplx);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K = 128 block reflectors: two consecutive 64-column panels share ONE trailing update.
+//   A2 <- (I - V2 T2^H V2^H)(I - V1 T1^H V1^H) A2  =  A2 - [V1 V2] [W1; W2]
+//   Y = [V1 V2]^H A2 (one split-K product with m = 128),  W1 = T1^H Y1,  W2 = T2^H (Y2 - (V2^H V1) W1)
+// so the rank-64 update (C read-modify-write bound, 27 TFLOP/s class) becomes a rank-128 one (40 TFLOP/s class) and half as
+// many passes over the trailing matrix are made.  The look-ahead works on pairs: the pair's reflectors go to the next
+// pair's 128 columns first, then the next pair is prepared (panel, narrow update, panel, Gram blocks) on the auxiliary
+// stream underneath the big update.  The panel kernel and T are unchanged, so R and the solution agree with the 64-wide
+// path to rounding.
+namespace {
+
+constexpr int PW2 = 2 * PW;
+
+struct QrPairWork {
+    cplx* V;      // rows x 128 (ld 128): [V1 | V2], V2 shifted down by 64 rows (its first 64 rows are zero)
+    cplx* Vt;     // 128 x ldvt
+    cplx* W;      // 128 x ldw
+    cplx* part;   // split-K partials
+    cplx* Gm;     // 64 x 64 scratch: V^H V of the panel being factored
+    cplx* T[2];   // compact-WY factors of the two panels
+    cplx* G12;    // V1^H V2
+    cplx* tau;    // 2 x 64
+    cplx* dots; cplx* currow; unsigned* bar; cplx* gslab;
+    int ldvt, ldw;
+};
+
+size_t pair_part_elems(int cols, int naug) {
+    const size_t ldw = (cols + naug + 7) / 8 * 8;
+    const size_t a = size_t(149) * PW * PW, b = size_t(12) * PW2 * ldw;
+    return a > b ? a : b;
+}
+
+QrPairWork carve_pair(void* work, int rows, int cols, int naug) {
+    QrPairWork w;
+    unsigned char* p = reinterpret_cast<unsigned char*>(work);
+    auto take = [&](size_t bytes) { void* q = p; p += align_up(bytes); return q; };
+    w.ldvt = (rows + 7) / 8 * 8;
+    w.ldw = (cols + naug + 7) / 8 * 8;
+    w.V = (cplx*)take(size_t(rows) * PW2 * sizeof(cplx));
+    w.Vt = (cplx*)take(size_t(PW2) * w.ldvt * sizeof(cplx));
+    w.W = (cplx*)take(size_t(PW2) * w.ldw * sizeof(cplx));
+    w.part = (cplx*)take(pair_part_elems(cols, naug) * sizeof(cplx));
+    w.Gm = (cplx*)take(size_t(PW) * PW * sizeof(cplx));
+    w.T[0] = (cplx*)take(size_t(PW) * PW * sizeof(cplx));
+    w.T[1] = (cplx*)take(size_t(PW) * PW * sizeof(cplx));
+    w.G12 = (cplx*)take(size_t(PW) * PW * sizeof(cplx));
+    w.tau = (cplx*)take(size_t(2) * PW * sizeof(cplx));
+    w.dots = (cplx*)take(size_t(2) * MAXG * PW * sizeof(cplx));
+    w.currow = (cplx*)take(size_t(2) * PW * sizeof(cplx));
+    w.bar = (unsigned*)take(256);
+    w.gslab = (cplx*)take(gslab_bytes(rows));
+    return w;
+}
+
+int splits_for(int mp, int n2, int kk, size_t part_cap) {
+    const int tiles = (n2 + 63) / 64 * (kk / 64);
+    int ns = (592 + tiles - 1) / tiles;                 // ~2 waves of 296 resident CTAs
+    const int cap = (mp + 255) / 256;                   // keep >= 256 k per slice
+    if (ns > cap) ns = cap;
+    const int fit = int(part_cap / (size_t(kk) * size_t(n2)));
+    if (ns > fit) ns = fit;
+    return ns < 1 ? 1 : ns;
+}
+
+// A2 (mp x n2) <- A2 - [V1 V2][W1; W2]  (kk = 128)  or the single-panel update with V1 alone (kk = 64)
+int pair_apply(cudaStream_t st, const QrPairWork& w, int kk, int mp, cplx* A2, int lda, int n2, size_t part_cap) {
+    if (n2 <= 0) return 0;
+    const int ns = splits_for(mp, n2, kk, part_cap);
+    int rc = zgemm_tn_splitk(st, true, kk, n2, mp, 1.0, w.V, PW2, A2, lda, 0.0, w.W, w.ldw, w.part, ns);            // Y = V^H A2
+    if (rc) return rc;
+    rc = zgemm_tn(st, true, PW, n2, PW, 1.0, w.T[0], PW, w.W, w.ldw, 0.0, w.W, w.ldw, GEMM_FULL);                   // W1 = T1^H Y1
+    if (rc) return rc;
+    if (kk == PW2) {
+        cplx* Y2 = w.W + size_t(PW) * w.ldw;
+        rc = zgemm_tn(st, true, PW, n2, PW, -1.0, w.G12, PW, w.W, w.ldw, 1.0, Y2, w.ldw, GEMM_FULL);                // Y2 -= (V2^H V1) W1
+        if (rc) return rc;
+        rc = zgemm_tn(st, true, PW, n2, PW, 1.0, w.T[1], PW, Y2, w.ldw, 0.0, Y2, w.ldw, GEMM_FULL);                 // W2 = T2^H Y2
+        if (rc) return rc;
+    }
+    return zgemm_tn(st, false, mp, n2, kk, -1.0, w.Vt, w.ldvt, w.W, w.ldw, 1.0, A2, lda, GEMM_FULL);                // A2 -= V W
+}
+
+// Factor the panel pair starting at column c0 (rows c0..rows-1 of A): returns the reflector width (64 or 128) in *kk.
+int pair_prepare(cudaStream_t st, const QrPairWork& w, cplx* A, int lda, int rows, int cols, int c0, size_t part_cap,
+                 double* logabs, int* kk) {
+    const int mp = rows - c0;
+    const int pwa = min(PW, cols - c0);
+    cplx* Ap = A + size_t(c0) * lda + c0;
+    // rows 0..63 of the second column block of V and columns 0..63 of rows 64..127 of V^T stay zero (V2 starts 64 rows lower)
+    MSPDE_CUDA(cudaMemset2DAsync(w.V + PW, PW2 * sizeof(cplx), 0, PW * sizeof(cplx), PW, st));
+    MSPDE_CUDA(cudaMemset2DAsync(w.Vt + size_t(PW) * w.ldvt, size_t(w.ldvt) * sizeof(cplx), 0, PW * sizeof(cplx), PW, st));
+    int rc = launch_panel(st, Ap, lda, mp, pwa, w.V, PW2, w.Vt, w.ldvt, w.tau, w.dots, w.currow, w.bar, w.gslab, logabs);
+    if (rc) return rc;
+    int ns_g = (mp + 127) / 128;
+    if (ns_g > 148) ns_g = 148;
+    rc = zgemm_tn_splitk(st, true, PW, PW, mp, 1.0, w.V, PW2, w.V, PW2, 0.0, w.Gm, PW, w.part, ns_g);
+    if (rc) return rc;
+    larft_kernel<<<1, 256, 2 * sizeof(cplx) * PW * (PW + 1), st>>>(w.Gm, w.tau, pwa, w.T[0]);
+    MSPDE_LAUNCH_CHECK();
+    const int c1 = c0 + PW;
+    if (c1 >= cols) { *kk = PW; return 0; }
+    const int pwb = min(PW, cols - c1);
+    rc = pair_apply(st, w, PW, mp, Ap + PW, lda, pwb, part_cap);             // reflector 1 -> the second panel's columns
+    if (rc) return rc;
+    cplx* V2 = w.V + size_t(PW) * PW2 + PW;
+    cplx* Vt2 = w.Vt + size_t(PW) * w.ldvt + PW;
+    rc = launch_panel(st, A + size_t(c1) * lda + c1, lda, mp - PW, pwb, V2, PW2, Vt2, w.ldvt, w.tau + PW, w.dots, w.currow, w.bar,
+                      w.gslab, logabs);
+    if (rc) return rc;
+    ns_g = (mp - PW + 127) / 128;
+    if (ns_g > 148) ns_g = 148;
+    rc = zgemm_tn_splitk(st, true, PW, PW, mp - PW, 1.0, V2, PW2, V2, PW2, 0.0, w.Gm, PW, w.part, ns_g);
+    if (rc) return rc;
+    larft_kernel<<<1, 256, 2 * sizeof(cplx) * PW * (PW + 1), st>>>(w.Gm, w.tau + PW, pwb, w.T[1]);
+    MSPDE_LAUNCH_CHECK();
+    ns_g = (mp + 127) / 128;
+    if (ns_g > 148) ns_g = 148;
+    rc = zgemm_tn_splitk(st, true, PW, PW, mp, 1.0, w.V, PW2, w.V + PW, PW2, 0.0, w.G12, PW, w.part, ns_g);     // G12 = V1^H V2
+    if (rc) return rc;
+    *kk = PW2;
+    return 0;
+}
+
+}  // namespace
+
+size_t qr_pair_work_bytes(int rows, int cols, int naug) {
+    const size_t ldvt = (rows + 7) / 8 * 8, ldw = (cols + naug + 7) / 8 * 8;
+    size_t b = 0;
+    b += align_up(size_t(rows) * PW2 * sizeof(cplx));
+    b += align_up(size_t(PW2) * ldvt * sizeof(cplx));
+    b += align_up(size_t(PW2) * ldw * sizeof(cplx));
+    b += align_up(pair_part_elems(cols, naug) * sizeof(cplx));
+    b += 4 * align_up(size_t(PW) * PW * sizeof(cplx));
+    b += align_up(size_t(2) * PW * sizeof(cplx));
+    b += align_up(size_t(2) * MAXG * PW * sizeof(cplx));
+    b += align_up(size_t(2) * PW * sizeof(cplx));
+    b += 256;
+    b += align_up(gslab_bytes(rows));
+    return b + 4096;
+}
+
+static int geqrf_aug_pairs(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, double* logabs,
+                           const QrLookAhead* la) {
+    if (init_attrs()) return -1;
+    const int ntot = cols + naug;
+    QrPairWork W[2] = {carve_pair(la->pair[0], la->pair_rows, la->pair_cols, la->pair_naug),
+                       carve_pair(la->pair[1], la->pair_rows, la->pair_cols, la->pair_naug)};
+    const size_t cap = pair_part_elems(la->pair_cols, la->pair_naug);
+    int kk = PW;
+    int rc = pair_prepare(st, W[0], A, lda, rows, cols, 0, cap, logabs, &kk);
+    if (rc) return rc;
+    int q = 0;
+    for (int c0 = 0; c0 < cols; c0 += PW2, ++q) {
+        const QrPairWork& cur = W[q & 1];
+        const int span = min(PW2, cols - c0);
+        const int mp = rows - c0;
+        cplx* Arow = A + size_t(c0) * lda;
+        const int next = c0 + span;
+        if (next < cols) {
+            const int nspan = min(PW2, cols - next);
+            rc = pair_apply(st, cur, kk, mp, Arow + next, lda, nspan, cap);                 // next pair's columns first
+            if (rc) return rc;
+            MSPDE_CUDA(cudaEventRecord(la->ev_a, st));
+            MSPDE_CUDA(cudaStreamWaitEvent(la->aux, la->ev_a, 0));
+            int kk_next = PW;
+            rc = pair_prepare(la->aux, W[(q + 1) & 1], A, lda, rows, cols, next, cap, logabs, &kk_next);
+            if (rc) return rc;
+            MSPDE_CUDA(cudaEventRecord(la->ev_b, la->aux));
+            rc = pair_apply(st, cur, kk, mp, Arow + next + nspan, lda, ntot - (next + nspan), cap);
+            if (rc) return rc;
+            MSPDE_CUDA(cudaStreamWaitEvent(st, la->ev_b, 0));
+            kk = kk_next;
+        } else {
+            rc = pair_apply(st, cur, kk, mp, Arow + next, lda, ntot - next, cap);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+static int g_qr_block = -1;    // -1: not chosen yet (environment MSPDE_QR_BLOCK = 64 | 128, default 128)
+int qr_block_width() {
+    if (g_qr_block < 0) {
+        const char* e = getenv("MSPDE_QR_BLOCK");
+        g_qr_block = (e && atoi(e) == PW) ? PW : 2 * PW;
+    }
+    return g_qr_block;
+}
+int set_qr_block_width(int k) {
+    if (k != PW && k != 2 * PW) { set_error("QR block-reflector width must be 64 or 128"); return -1; }
+    g_qr_block = k;
+    return 0;
+}
+
 // Householder QR of the leading `cols` columns of Aaug (rows x (cols + naug)), trailing columns get Q^H applied.
 // logabs (device, optional) accumulates sum log |r_jj|.
 int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs,
               const QrLookAhead* la) {
     if (logabs) MSPDE_CUDA(cudaMemsetAsync(logabs, 0, sizeof(double), st));
     const int ntot = cols + naug;
+    if (qr_block_width() == 2 * PW && la && la->pair[0] && la->pair[1] && cols > 2 * PW && rows <= la->pair_rows && cols <= la->pair_cols &&
+        naug <= la->pair_naug)
+        return geqrf_aug_pairs(st, A, lda, rows, cols, naug, logabs, la);
     if (la == nullptr || la->work2 == nullptr || cols <= PW) {
         for (int c0 = 0; c0 < cols; c0 += PW) {
             const int pw = min(PW, cols - c0);

@@ -39,7 +39,14 @@ struct QrLookAhead {        // auxiliary stream, events and second panel workspa
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     void* work2 = nullptr;  // qr_work_bytes(rows, cols) like `work`
+    // K = 128 path (two 64-column panels per trailing update): two pair workspaces of qr_pair_work_bytes(pair_rows, pair_cols,
+    // pair_naug) bytes each; geqrf_aug uses them for any problem that fits those sizes
+    void* pair[2] = {nullptr, nullptr};
+    int pair_rows = 0, pair_cols = 0, pair_naug = 0;
 };
+size_t qr_pair_work_bytes(int rows, int cols, int naug);
+int qr_block_width();
+int set_qr_block_width(int k);
 int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs,
               const QrLookAhead* la = nullptr);
 int qr_panel_factor(cudaStream_t st, cplx* Ap, int lda, int mp, int pw, int rows, int cols, void* work, double* logabs);

@@ -72,3 +72,12 @@ def set_gemm_pre_min(v: int):
 
 def get_gemm_pre_min() -> int:
     return int(lib().mspde_get_gemm_pre_min())
+
+
+def set_qr_block(width: int):
+    """64 or 128: block-reflector width of the Householder QR (include/mspde.h: mspde_set_qr_block)."""
+    check(lib().mspde_set_qr_block(int(width)), "set_qr_block")
+
+
+def get_qr_block() -> int:
+    return int(lib().mspde_get_qr_block())

@@ -545,13 +545,14 @@ def test_simulation_surface_small():
     with tempfile.TemporaryDirectory() as d:
         fn = sim.save(os.path.join(d, "result_0.hdf5"))
         last = io.load_last_samples(fn)
-        assert len(last) == 3 and np.array_equal(last[2], sim.Layers[2].samples_history[sim.Layers[2].i_record - 1])
+        # the file holds complex64 histories, as the reference's does (image_cupy.py:729, 939)
+        assert len(last) == 3 and np.array_equal(last[2], sim.Layers[2].samples_history[sim.Layers[2].i_record - 1].astype(np.complex64))
         sim2 = im.Simulation(n_layers=3, n_samples=3, n=4, n_extended=64, beta=0.5, kappa=5e9, sigma_0=4e7, sigma_v=3.2e4,
                              sigma_scaling=0.4, meas_std=0.2, evaluation_interval=2, printProgress=False, seed=4,
                              burn_percentage=25.0, enable_step_adaptation=True, pcn_variant="dunlop", phantom_name="shepp.png",
                              n_theta=8)
         io.initialize_from_file(sim2, fn)
-        assert rel(sim2.Layers[2].current_sample.cpu(), last[2]) < 1e-15
+        assert rel(sim2.Layers[2].current_sample.cpu(), last[2].astype(np.complex128)) < 1e-15
         img = io.initialize_using_FBP(sim2)
         assert img.shape == (127, 127) and np.isfinite(img).all()
         sim2.pcn.set_chol_epsilon(1e-6)
@@ -939,3 +940,32 @@ def test_presummed_3m_kernel_is_bit_identical(lib):
     finally:
         _ffi.set_gemm_mode(mode0)
         _ffi.set_gemm_pre_min(pre0)
+
+
+@pytest.mark.parametrize("rows,cols", [(300, 129), (1100, 200), (2000, 449), (700, 700)])
+def test_qr_block_reflector_widths_agree(rows, cols):
+    """util.lstsq through the Householder QR with rank-128 block reflectors (two panels per trailing update, the default) and
+    with rank-64 ones (every panel on its own): same panel kernel, solutions agree to rounding and match cuSOLVER's lstsq.
+    Sizes cover an odd number of panels, a last panel of one column, and a square system."""
+    from mspde import _ffi
+    from mspde.core import MspdeContext
+    n = int(np.ceil((np.sqrt(cols) + 1) / 2))
+    while (2 * n - 1) ** 2 < cols:
+        n += 1
+    N = (2 * n - 1) ** 2
+    ctx = MspdeContext(n, 64, max(rows - N, 1) + 64, 3)
+    assert ctx.M + ctx.N >= rows and ctx.N >= cols
+    a = crandn(rows, cols, seed=rows) + 0.5 * torch.eye(rows, cols, dtype=torch.complex128, device="cuda")
+    b = crandn(rows, seed=cols)
+    default = _ffi.get_qr_block()
+    sols = {}
+    try:
+        for width in (64, 128):
+            _ffi.set_qr_block(width)
+            sols[width] = ctx.lstsq(a, b).clone()
+    finally:
+        _ffi.set_qr_block(default)
+    ref = torch.linalg.lstsq(a, b.unsqueeze(1)).solution.squeeze(1)
+    assert rel(sols[128].cpu(), ref.cpu()) < 1e-11 and rel(sols[64].cpu(), ref.cpu()) < 1e-11
+    assert rel(sols[128].cpu(), sols[64].cpu()) < 1e-12
+    ctx.close()
