@@ -657,10 +657,11 @@ def main():
                                                                  "note": "same launch counted at 8 flop per complex multiply-add (SURVEY 8d's "
                                                                          "ZHERK = 4 n^2 k), the convention ZGEMM rates are quoted in; above 1.0 "
                                                                          "under 3M because the kernel's algorithm needs 6"},
-                    "traffic": 15.5e9 if gemm_mode == _ffi.GEMM_3M else 13.1e9,
+                    "traffic": 15.44e9 if gemm_mode == _ffi.GEMM_3M else 13.1e9,
                     "traffic_source": "dram__bytes_read+write of this launch from one ncu --set full capture: "
-                                      + ("profiles/r01_zgemm3m_k1024_full.ncu-rep (14.47e9 read + 1.04e9 written; algorithmic 0.73e9 + 1.05e9: "
-                                         "operand panels are re-read from DRAM when a wave's working set leaves the L2, 86 % L2 hit rate)"
+                                      + ("profiles/r02_zgemm3m_full.ncu-rep (14.40e9 read + 1.05e9 written; algorithmic 0.73e9 + 1.05e9: "
+                                         "operand panels are re-read from DRAM when a wave's working set leaves the L2, 85.5 % L2 hit rate; "
+                                         "DRAM runs at ~4 % of its peak, the tensor pipe at 88.6 % active)"
                                          if gemm_mode == _ffi.GEMM_3M else
                                          "profiles/r01_zgemm_full_v2.ncu-rep (grouped tile rasterisation; 56.2e9 before it)"),
                     "ms_per_launch": ms_k,

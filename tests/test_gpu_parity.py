@@ -835,7 +835,7 @@ def test_block_distributed_phi_matches_single_gpu(toy):
         rhs = crandn(ctx.M + ctx.N, seed=12)
         v1 = ctx.gibbs_lstsq(L, rhs)
         v2 = DistQR(ctx.device).lstsq([ctx.H, L], rhs)
-        assert torch.equal(v1, v2)
+        assert rel(v2.cpu(), v1.cpu()) < 1e-12             # same panel kernel; 64-wide updates there, rank-128 pairs on one GPU
     finally:
         if created:
             dist.destroy_process_group()
