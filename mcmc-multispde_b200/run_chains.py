@@ -5,8 +5,10 @@
          --n-layers 3 --n-theta 90 --n-samples 1000 --out chains.npz
 
 Chain c runs on rank c mod G with seed `seed + c` (the scheme of /root/reference/Legacy/runNumbaParallel.py:24-43, there
-with mpi4py); there is no communication until the final all_gather of every layer's recorded half-samples and the
-sum-reduction of the acceptance counters (121-136 there).  Works on a single GPU without torchrun as well."""
+with mpi4py); a rank's chains share one context and are stepped round-robin (mspde.parallel.MultiChain).  There is no
+communication until the final all_gather of every layer's recorded half-samples, the sum-reduction of the acceptance
+counters and the pooling of the per-layer Welford field statistics (121-136, 165-180 there).  Works on a single GPU without
+torchrun as well."""
 import argparse
 import os
 import sys
@@ -42,29 +44,47 @@ def main(argv=None):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     mine = parallel.shard_chains(args.chains, world, rank)
-    hist, accepted, steps = [], 0, 0
+    nr = 2 * args.n * args.n - 2 * args.n + 1
     t0 = time.perf_counter()
-    for c in mine:
+    accepted = steps = 0
+    stats = None
+    if mine:
+        # one Simulation (context: H, HtH, y, workspaces) per GPU, shared by all of this rank's chains (parallel.MultiChain)
         sim = im.Simulation(n_layers=args.n_layers, n_samples=args.n_samples, n=args.n, n_extended=args.n_extended, beta=args.beta,
                             kappa=5e9, sigma_0=4e7, sigma_v=3.2e4, sigma_scaling=0.4, meas_std=0.2,
                             evaluation_interval=args.evaluation_interval, printProgress=False,
-                            seed=parallel.chain_seed(args.seed, c), burn_percentage=25.0, enable_step_adaptation=True,
+                            seed=parallel.chain_seed(args.seed, mine[0]), burn_percentage=25.0, enable_step_adaptation=True,
                             pcn_variant="dunlop", phantom_name="shepp.png", meas_type="tomo", n_theta=args.n_theta, verbose=False,
                             device=local)
         sim.pcn.set_chol_epsilon(1e-6)
-        sim.run()
-        hist.append(np.stack([lay.samples_history for lay in sim.Layers]))      # [layers, samples, n_ravel]
-        accepted += sim.accepted_count
-        steps += args.n_samples
-        sim.pcn.ctx.close()
-        del sim
-        torch.cuda.empty_cache()
+        mc = parallel.MultiChain(sim, mine, base_seed=args.seed, accumulate_stats=True)
+        for _ in range(args.n_samples):
+            mc.step_all()
+        local_hist = torch.as_tensor(mc.histories())                               # [local chains, layers, samples, n_ravel]
+        accepted, steps = mc.accepted_and_steps()
+    else:
+        mc = None
+        local_hist = torch.zeros((0, args.n_layers, args.n_samples, nr), dtype=torch.complex128)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    local_hist = torch.as_tensor(np.stack(hist)) if hist else torch.zeros((0, args.n_layers, args.n_samples, 2 * args.n * args.n - 2 * args.n + 1),
-                                                                       dtype=torch.complex128)
     full = parallel.gather_samples(local_hist.to(dev), args.chains, world)     # [chains, layers, samples, n_ravel]
     acc = parallel.pooled_acceptance(accepted, steps)
+    if mc is not None and world == 1:
+        stats = mc.pooled_field_statistics()
+    elif world > 1:
+        # every rank takes part in the pooled-statistics collectives (a rank without chains contributes count 0)
+        if mc is None:
+            m = 2 * args.n_extended - 1
+            z = torch.zeros((m, m), dtype=torch.float64, device=dev)
+            stats = []
+            for _ in range(args.n_layers):
+                res = {}
+                for name in ("u", "ell"):
+                    n_, mean_, m2_ = parallel.pool_welford(0, z, z)
+                    res.update({"count": n_, name + "_mean": mean_, name + "_var": m2_ / max(n_, 1)})
+                stats.append(res)
+        else:
+            stats = mc.pooled_field_statistics()
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -73,7 +93,13 @@ def main(argv=None):
         print(f"{args.chains} chains x {args.n_samples} samples on {world} GPU(s): {rate:.3f} iterations/s aggregate, "
               f"pooled acceptance {acc:.3f}, gathered {tuple(full.shape)}")
         if args.out:
-            np.savez_compressed(args.out, samples=full.cpu().numpy(), acceptance=acc, chains=args.chains)
+            extra = {}
+            if stats is not None:
+                for k, st in enumerate(stats):
+                    extra.update({f"layer{k}_u_mean": st["u_mean"].cpu().numpy(), f"layer{k}_u_var": st["u_var"].cpu().numpy(),
+                                  f"layer{k}_ell_mean": st["ell_mean"].cpu().numpy(), f"layer{k}_ell_var": st["ell_var"].cpu().numpy()})
+                extra["stats_count"] = stats[0]["count"]
+            np.savez_compressed(args.out, samples=full.cpu().numpy(), acceptance=acc, chains=args.chains, **extra)
     if world > 1:
         dist.destroy_process_group()
 

@@ -969,3 +969,67 @@ def test_qr_block_reflector_widths_agree(rows, cols):
     assert rel(sols[128].cpu(), ref.cpu()) < 1e-11 and rel(sols[64].cpu(), ref.cpu()) < 1e-11
     assert rel(sols[128].cpu(), sols[64].cpu()) < 1e-12
     ctx.close()
+
+
+def test_multichain_runner_matches_chains_run_alone():
+    """parallel.MultiChain (configs[3]: many chains per GPU through ONE shared context) against the same chains run alone:
+    with injected noise every chain's accept flags, Phi values and samples are bit-identical, and the pooled Welford field
+    statistics equal the statistics of all chains' samples taken together."""
+    from mspde import image as im, parallel
+
+    def make(seed, n_samples=5):
+        sim = im.Simulation(n_layers=3, n_samples=n_samples, n=4, n_extended=64, beta=0.5, kappa=5e9, sigma_0=4e7, sigma_v=3.2e4,
+                            sigma_scaling=0.4, meas_std=0.2, evaluation_interval=2, printProgress=False, seed=seed, burn_percentage=25.0,
+                            enable_step_adaptation=True, pcn_variant="dunlop", phantom_name="shepp.png", n_theta=8)
+        sim.pcn.set_chol_epsilon(1e-6)
+        return sim
+    ids, base = [0, 1, 2], 11
+    sim = make(parallel.chain_seed(base, ids[0]))
+    mc = parallel.MultiChain(sim, ids, base_seed=base, accumulate_stats=True)
+    hp = o.Hyper(n_layers=3, n=4, n_ext=64, n_theta=8)
+    ft = o.FourierTables(4, 64)
+    streams = [o.NoiseStream(100 + c, 3, ft.n_ravel, sim.pcn.ctx.M) for c in ids]
+    to = sim.pcn.ctx.to_dev
+    # snapshot every chain's initial state, then step all chains together
+    snaps = [[(l._noise_cur.clone(), l._u_cur.clone(), l._u_new.clone(), l.LMat.current_L.clone() if k else None)
+              for k, l in enumerate(ch["Layers"])] for ch in mc.chains]
+    noises = [[s.draw_iteration() for _ in range(4)] for s in streams]
+    log = [[] for _ in ids]
+    for it in range(4):
+        nz = [([to(w) for w in noises[c][it]["w_half"]], noises[c][it]["log_u"], to(noises[c][it]["w_last"]), to(noises[c][it]["e"]))
+              for c in range(len(ids))]
+        betas = [ch["beta"] for ch in mc.chains]
+        mc.step_all(noise=nz)
+        for c, ch in enumerate(mc.chains):
+            log[c].append((betas[c], [l._u_new.clone() for l in ch["Layers"]], [l._u_cur.clone() for l in ch["Layers"]]))
+    acc_multi, steps_multi = mc.accepted_and_steps()
+    assert steps_multi == 12
+    # now every chain alone, in a fresh context, from the same initial state with the same noise and step sizes
+    for c, cid in enumerate(ids):
+        solo = make(parallel.chain_seed(base, cid))
+        for k, l in enumerate(solo.Layers):
+            nc, uc, un, Lc = snaps[c][k]
+            l._noise_cur.copy_(nc); l._noise_new.copy_(nc); l._u_cur.copy_(uc); l._u_new.copy_(un)
+            if k:
+                l.LMat.current_L.copy_(Lc)
+        for it in range(4):
+            solo.pcn.beta, solo.pcn.betaZ = log[c][it][0], float(np.sqrt(max(0.0, 1 - log[c][it][0] ** 2)))
+            n_ = noises[c][it]
+            solo.pcn.one_step(solo.Layers, noise=([to(w) for w in n_["w_half"]], n_["log_u"], to(n_["w_last"]), to(n_["e"])))
+            for k in range(3):
+                assert torch.equal(solo.Layers[k]._u_new, log[c][it][1][k]), (cid, it, k)
+                assert torch.equal(solo.Layers[k]._u_cur, log[c][it][2][k]), (cid, it, k)
+        solo.pcn.ctx.close()
+    # pooled statistics == statistics over all recorded samples of all chains
+    pooled = mc.pooled_field_statistics()
+    assert pooled[0]["count"] == 12
+    fields = []
+    for ch in mc.chains:
+        lay = ch["Layers"][1]
+        for r in range(lay.i_record):
+            u = o.symmetrize(lay.samples_history[r])
+            fields.append(o.irfft2(o.from_u_2D_ravel_to_uHalf_2D(u, 4), ft))
+    F = np.stack(fields)
+    assert rel(pooled[1]["u_mean"].cpu(), F.mean(0)) < 1e-11
+    assert rel(pooled[1]["u_var"].cpu(), F.var(0)) < 1e-10
+    sim.pcn.ctx.close()
