@@ -170,6 +170,16 @@ int mspde_qr_apply(void* stream, int mp, int rows, int cols, void* work, void* A
 int mspde_lu_panel(void* stream, void* Ap, int lda, int mp, int pw, int goff, int n, int ntot, void* work, int* info_dev,
                    double* logabs_dev);
 int mspde_lu_apply(void* stream, int mp, int pw, int n, int ntot, void* work, void* A12, int lda, int n2);
+/* Rank-128 variant for the block-distributed QR over 128-column blocks: the owner of a block factors BOTH of its 64-column
+ * panels (mspde_qr_pair_prepare: Ap = top-left element of the block, mp rows from there down, span <= 128 pivot columns;
+ * *kk_host <- 64 or 128), broadcasts the five pieces named by mspde_qr_pair_work_layout (byte offset, byte size pairs: V
+ * (rows x 128), V^T, T1, T2, V1^H V2), and every rank applies the pair to its own columns with ONE rank-kk update
+ * (mspde_qr_pair_apply).  The workspace is sized / laid out for (wrows, wcols, wnaug) = the whole problem. */
+long long mspde_qr_pair_work_bytes(int rows, int cols, int naug);
+int mspde_qr_pair_work_layout(int rows, int cols, int naug, void* work, long long* out10_host);
+int mspde_qr_pair_prepare(void* stream, void* work, int wrows, int wcols, int wnaug, void* Ap, int lda, int mp, int span,
+                          double* logabs_dev, int* kk_host);
+int mspde_qr_pair_apply(void* stream, void* work, int wrows, int wcols, int wnaug, int kk, int mp, void* A2, int lda, int n2);
 /* x <- R^-1 d for the upper triangle R of A[0:n,0:n], d = column dcol of A (ztrsm call site, extra_linalg.py:102). */
 int mspde_trsv_upper(void* stream, void* A, int lda, int n, int dcol, void* x);
 

@@ -347,6 +347,18 @@ int mspde_qr_panel(void* stream, void* Ap, int lda, int mp, int pw, int rows, in
 int mspde_qr_apply(void* stream, int mp, int rows, int cols, void* work, void* A2, int lda, int n2) {
     return qr_panel_apply((cudaStream_t)stream, mp, rows, cols, work, (cplx*)A2, lda, n2);
 }
+long long mspde_qr_pair_work_bytes(int rows, int cols, int naug) { return (long long)qr_pair_work_bytes(rows, cols, naug); }
+int mspde_qr_pair_work_layout(int rows, int cols, int naug, void* work, long long* out10) {
+    qr_pair_work_layout(rows, cols, naug, work, out10);
+    return 0;
+}
+int mspde_qr_pair_prepare(void* stream, void* work, int wrows, int wcols, int wnaug, void* Ap, int lda, int mp, int span,
+                          double* logabs_dev, int* kk_host) {
+    return qr_pair_prepare_at((cudaStream_t)stream, work, wrows, wcols, wnaug, (cplx*)Ap, lda, mp, span, logabs_dev, kk_host);
+}
+int mspde_qr_pair_apply(void* stream, void* work, int wrows, int wcols, int wnaug, int kk, int mp, void* A2, int lda, int n2) {
+    return qr_pair_apply_at((cudaStream_t)stream, work, wrows, wcols, wnaug, kk, mp, (cplx*)A2, lda, n2);
+}
 int mspde_lu_panel(void* stream, void* Ap, int lda, int mp, int pw, int goff, int n, int ntot, void* work, int* info_dev,
                    double* logabs_dev) {
     return lu_panel_factor((cudaStream_t)stream, (cplx*)Ap, lda, mp, pw, goff, n, ntot, work, info_dev, logabs_dev);

@@ -502,12 +502,11 @@ int pair_apply(cudaStream_t st, const QrPairWork& w, int kk, int mp, cplx* A2, i
     return zgemm_tn(st, false, mp, n2, kk, -1.0, w.Vt, w.ldvt, w.W, w.ldw, 1.0, A2, lda, GEMM_FULL);                // A2 -= V W
 }
 
-// Factor the panel pair starting at column c0 (rows c0..rows-1 of A): returns the reflector width (64 or 128) in *kk.
-int pair_prepare(cudaStream_t st, const QrPairWork& w, cplx* A, int lda, int rows, int cols, int c0, size_t part_cap,
-                 double* logabs, int* kk) {
-    const int mp = rows - c0;
-    const int pwa = min(PW, cols - c0);
-    cplx* Ap = A + size_t(c0) * lda + c0;
+// Factor the panel pair whose top-left element is Ap (mp rows below and including it, `span` <= 128 pivot columns): returns the
+// reflector width (64 or 128) in *kk.
+int pair_prepare(cudaStream_t st, const QrPairWork& w, cplx* Ap, int lda, int mp, int span, size_t part_cap, double* logabs,
+                 int* kk) {
+    const int pwa = min(PW, span);
     // rows 0..63 of the second column block of V and columns 0..63 of rows 64..127 of V^T stay zero (V2 starts 64 rows lower)
     MSPDE_CUDA(cudaMemset2DAsync(w.V + PW, PW2 * sizeof(cplx), 0, PW * sizeof(cplx), PW, st));
     MSPDE_CUDA(cudaMemset2DAsync(w.Vt + size_t(PW) * w.ldvt, size_t(w.ldvt) * sizeof(cplx), 0, PW * sizeof(cplx), PW, st));
@@ -519,14 +518,13 @@ int pair_prepare(cudaStream_t st, const QrPairWork& w, cplx* A, int lda, int row
     if (rc) return rc;
     larft_kernel<<<1, 256, 2 * sizeof(cplx) * PW * (PW + 1), st>>>(w.Gm, w.tau, pwa, w.T[0]);
     MSPDE_LAUNCH_CHECK();
-    const int c1 = c0 + PW;
-    if (c1 >= cols) { *kk = PW; return 0; }
-    const int pwb = min(PW, cols - c1);
+    if (span <= PW || mp <= PW) { *kk = PW; return 0; }
+    const int pwb = span - PW;
     rc = pair_apply(st, w, PW, mp, Ap + PW, lda, pwb, part_cap);             // reflector 1 -> the second panel's columns
     if (rc) return rc;
     cplx* V2 = w.V + size_t(PW) * PW2 + PW;
     cplx* Vt2 = w.Vt + size_t(PW) * w.ldvt + PW;
-    rc = launch_panel(st, A + size_t(c1) * lda + c1, lda, mp - PW, pwb, V2, PW2, Vt2, w.ldvt, w.tau + PW, w.dots, w.currow, w.bar,
+    rc = launch_panel(st, Ap + size_t(PW) * lda + PW, lda, mp - PW, pwb, V2, PW2, Vt2, w.ldvt, w.tau + PW, w.dots, w.currow, w.bar,
                       w.gslab, logabs);
     if (rc) return rc;
     ns_g = (mp - PW + 127) / 128;
@@ -561,6 +559,29 @@ size_t qr_pair_work_bytes(int rows, int cols, int naug) {
     return b + 4096;
 }
 
+// Pair-level pieces for the block-distributed driver (mspde/dist.py: DistQR over 128-column blocks): the owner of a block
+// prepares the pair (both panels, their T factors, V1^H V2), broadcasts V, V^T, T1, T2, G12 (qr_pair_work_layout) and every
+// rank applies it to its own columns.  The workspace is laid out for (wrows, wcols, wnaug) like the single-GPU path's.
+int qr_pair_prepare_at(cudaStream_t st, void* work, int wrows, int wcols, int wnaug, cplx* Ap, int lda, int mp, int span,
+                       double* logabs, int* kk_host) {
+    if (init_attrs()) return -1;
+    QrPairWork w = carve_pair(work, wrows, wcols, wnaug);
+    return pair_prepare(st, w, Ap, lda, mp, span, pair_part_elems(wcols, wnaug), logabs, kk_host);
+}
+int qr_pair_apply_at(cudaStream_t st, void* work, int wrows, int wcols, int wnaug, int kk, int mp, cplx* A2, int lda, int n2) {
+    QrPairWork w = carve_pair(work, wrows, wcols, wnaug);
+    return pair_apply(st, w, kk, mp, A2, lda, n2, pair_part_elems(wcols, wnaug));
+}
+void qr_pair_work_layout(int wrows, int wcols, int wnaug, void* work, long long* out10) {
+    QrPairWork w = carve_pair(work, wrows, wcols, wnaug);
+    unsigned char* base = reinterpret_cast<unsigned char*>(work);
+    out10[0] = reinterpret_cast<unsigned char*>(w.V) - base;    out10[1] = (long long)wrows * PW2 * sizeof(cplx);
+    out10[2] = reinterpret_cast<unsigned char*>(w.Vt) - base;   out10[3] = (long long)PW2 * w.ldvt * sizeof(cplx);
+    out10[4] = reinterpret_cast<unsigned char*>(w.T[0]) - base; out10[5] = (long long)PW * PW * sizeof(cplx);
+    out10[6] = reinterpret_cast<unsigned char*>(w.T[1]) - base; out10[7] = (long long)PW * PW * sizeof(cplx);
+    out10[8] = reinterpret_cast<unsigned char*>(w.G12) - base;  out10[9] = (long long)PW * PW * sizeof(cplx);
+}
+
 static int geqrf_aug_pairs(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, double* logabs,
                            const QrLookAhead* la) {
     if (init_attrs()) return -1;
@@ -569,7 +590,7 @@ static int geqrf_aug_pairs(cudaStream_t st, cplx* A, int lda, int rows, int cols
                        carve_pair(la->pair[1], la->pair_rows, la->pair_cols, la->pair_naug)};
     const size_t cap = pair_part_elems(la->pair_cols, la->pair_naug);
     int kk = PW;
-    int rc = pair_prepare(st, W[0], A, lda, rows, cols, 0, cap, logabs, &kk);
+    int rc = pair_prepare(st, W[0], A, lda, rows, min(PW2, cols), cap, logabs, &kk);
     if (rc) return rc;
     int q = 0;
     for (int c0 = 0; c0 < cols; c0 += PW2, ++q) {
@@ -585,7 +606,7 @@ static int geqrf_aug_pairs(cudaStream_t st, cplx* A, int lda, int rows, int cols
             MSPDE_CUDA(cudaEventRecord(la->ev_a, st));
             MSPDE_CUDA(cudaStreamWaitEvent(la->aux, la->ev_a, 0));
             int kk_next = PW;
-            rc = pair_prepare(la->aux, W[(q + 1) & 1], A, lda, rows, cols, next, cap, logabs, &kk_next);
+            rc = pair_prepare(la->aux, W[(q + 1) & 1], A + size_t(next) * lda + next, lda, rows - next, nspan, cap, logabs, &kk_next);
             if (rc) return rc;
             MSPDE_CUDA(cudaEventRecord(la->ev_b, la->aux));
             rc = pair_apply(st, cur, kk, mp, Arow + next + nspan, lda, ntot - (next + nspan), cap);

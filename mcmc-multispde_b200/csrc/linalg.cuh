@@ -45,6 +45,10 @@ struct QrLookAhead {        // auxiliary stream, events and second panel workspa
     int pair_rows = 0, pair_cols = 0, pair_naug = 0;
 };
 size_t qr_pair_work_bytes(int rows, int cols, int naug);
+int qr_pair_prepare_at(cudaStream_t st, void* work, int wrows, int wcols, int wnaug, cplx* Ap, int lda, int mp, int span,
+                       double* logabs, int* kk_host);
+int qr_pair_apply_at(cudaStream_t st, void* work, int wrows, int wcols, int wnaug, int kk, int mp, cplx* A2, int lda, int n2);
+void qr_pair_work_layout(int wrows, int wcols, int wnaug, void* work, long long* out10);
 int qr_block_width();
 int set_qr_block_width(int k);
 int geqrf_aug(cudaStream_t st, cplx* A, int lda, int rows, int cols, int naug, void* work, double* logabs,

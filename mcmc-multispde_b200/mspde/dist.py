@@ -304,7 +304,9 @@ class BlockCols:
 
     NB = 64
 
-    def __init__(self, rows, ntot, world, rank, device):
+    def __init__(self, rows, ntot, world, rank, device, nb=None):
+        if nb is not None:
+            self.NB = int(nb)            # instance override: the rank-128 QR distributes 128-column blocks
         nb = self.NB
         self.rows, self.ntot, self.world, self.rank = rows, ntot, world, rank
         self.nblk = (ntot + nb - 1) // nb
@@ -352,7 +354,7 @@ class _DistFactor:
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        for name in ("mspde_qr_work_bytes", "mspde_lu_work_bytes"):
+        for name in ("mspde_qr_work_bytes", "mspde_lu_work_bytes", "mspde_qr_pair_work_bytes"):
             getattr(self.lib, name).restype = ctypes.c_longlong
 
     def _bcast_bytes(self, work, off, size, src):
@@ -466,14 +468,18 @@ class DistQR(_DistFactor):
         return run_to_completion(self.lstsq_gen(blocks, rhs))
 
     def lstsq_gen(self, blocks, rhs):
+        """Rank-128 block reflectors: the matrix is distributed over 128-column blocks; the owner of a block factors both of
+        its 64-column panels (mspde_qr_pair_prepare), broadcasts V (live rows x 128), V^T, T1, T2 and V1^H V2, and every rank
+        applies the pair to its own columns with one rank-128 update (mspde_qr_pair_apply).  Look-ahead of one block."""
         rows = sum(b.shape[0] for b in blocks)
         n = blocks[0].shape[1]
         many = isinstance(rhs, (list, tuple))
         rhs_list = list(rhs) if many else [rhs]
-        ntot = n + len(rhs_list)
-        mat = BlockCols(rows, ntot, self.world, self.rank, self.device)
+        naug = len(rhs_list)
+        ntot = n + naug
+        nbk = 128
+        mat = BlockCols(rows, ntot, self.world, self.rank, self.device, nb=nbk)
         r0 = 0
-        nbk = mat.NB
         for blk in blocks:                     # fill the owned columns block row by block row (no stacked copy is formed)
             for b in mat.owned:
                 g0, w, l0 = b * nbk, mat.width(b), mat.col0[b]
@@ -485,38 +491,42 @@ class DistQR(_DistFactor):
             b = (n + j) // nbk
             if b in mat.col0:
                 mat.data[:, mat.col0[b] + (n + j - b * nbk)] = rj
-        nbytes = int(self.lib.mspde_qr_work_bytes(rows, n))
+        nbytes = int(self.lib.mspde_qr_pair_work_bytes(rows, n, naug))
         works = [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
-        lay = (ctypes.c_longlong * 6)()
-        self.lib.mspde_qr_work_layout(rows, n, _ffi.ptr(works[0]), lay)
+        lay = (ctypes.c_longlong * 10)()
+        self.lib.mspde_qr_pair_work_layout(rows, n, naug, _ffi.ptr(works[0]), lay)
         st = _ffi.current_stream
         npan = (n + nbk - 1) // nbk
-        dims = lambda p: (p * nbk, min(nbk, n - p * nbk), rows - p * nbk)     # c0, pw, mp
+        dims = lambda p: (p * nbk, min(nbk, n - p * nbk), rows - p * nbk)     # c0, span, mp
+        kks = {}
 
         def factor(p):
-            c0, pw, mp = dims(p)
-            _ffi.check(self.lib.mspde_qr_panel(st(), mat.ptr(c0, mat.col0[p]), mat.ld, mp, pw, rows, n, _ffi.ptr(works[p % 2]), None),
-                       "qr_panel")
+            c0, span, mp = dims(p)
+            kk = ctypes.c_int(0)
+            _ffi.check(self.lib.mspde_qr_pair_prepare(st(), _ffi.ptr(works[p % 2]), rows, n, naug, mat.ptr(c0, mat.col0[p]), mat.ld, mp,
+                                                      span, None, ctypes.byref(kk)), "qr_pair_prepare")
 
         def publish(p):
-            c0, pw, mp = dims(p)
+            c0, span, mp = dims(p)
+            kks[p] = 128 if (span > 64 and mp > 64) else 64            # what mspde_qr_pair_prepare decided, known to every rank
             w, owner = works[p % 2], p % self.world
             self._bcast_bytes(w, lay[0], mp * nbk * 16, owner)             # V: only the mp live rows
-            self._bcast_bytes(w, lay[2], lay[3], owner)                    # V^T
-            self._bcast_bytes(w, lay[4], lay[5], owner)                    # T
+            for k in (2, 4, 6, 8):                                         # V^T, T1, T2, V1^H V2
+                self._bcast_bytes(w, lay[k], lay[k + 1], owner)
 
         def apply(p, start, n2):
-            c0, pw, mp = dims(p)
+            c0, span, mp = dims(p)
             if n2 > 0:
-                _ffi.check(self.lib.mspde_qr_apply(st(), mp, rows, n, _ffi.ptr(works[p % 2]), mat.ptr(c0, start), mat.ld, n2), "qr_apply")
+                _ffi.check(self.lib.mspde_qr_pair_apply(st(), _ffi.ptr(works[p % 2]), rows, n, naug, kks[p], mp, mat.ptr(c0, start),
+                                                        mat.ld, n2), "qr_pair_apply")
 
-        # look-ahead of one panel (see DistLU.solve_gen)
+        # look-ahead of one block (see DistLU.solve_gen)
         if self.rank == 0:
             factor(0)
         publish(0)
         for p in range(npan):
-            c0, pw, mp = dims(p)
-            start, n2 = mat.right_of(p, pw)
+            c0, span, mp = dims(p)
+            start, n2 = mat.right_of(p, span)
             if p + 1 < npan:
                 if self.rank == (p + 1) % self.world:
                     wn = mat.width(p + 1)
