@@ -276,7 +276,8 @@ def config5_block(cfg, dev, rank, world, steps, warmup, fp64_peak, selfcheck_n=(
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     sec = float(tt.item()) / steps
     out.update({"value": 1.0 / sec, "ms_per_step": 1e3 * sec, "gemm_scheme": "3m" if _ffi.get_gemm_mode() == _ffi.GEMM_3M else "4m",
-                "steps_detail": [dict(seconds=r[0], accepted=bool(r[1]["accepted"]), phi_cur=r[1]["phi_cur"], phi_new=r[1]["phi_new"])
+                "steps_detail": [dict(seconds=r[0], accepted=bool(r[1]["accepted"]), phi_cur=r[1]["phi_cur"], phi_new=r[1]["phi_new"],
+                                      phase_s=r[1].get("phase_s"))
                                  for r in runs],
                 "finite": bool(all(np.isfinite(r[1]["phi_new"]) for r in runs) and torch.isfinite(chain.u_new[-1].abs()).all()),
                 "roofline": {"bound": "tensor", "achieved": f_iter / sec / 1e12 / world, "peak": fp64_peak, "unit": "TFLOP/s per GPU",

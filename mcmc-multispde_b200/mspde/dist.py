@@ -642,10 +642,12 @@ class DistPCN:
     def one_step(self, w_half, log_u, w_last, e):
         """One iteration with injected noise (device tensors: K-1 half vectors, last layer's half vector, M normals).
         Returns dict(accepted, log_ratio, phi_cur, phi_new); raises numpy.linalg.LinAlgError like the single-GPU path."""
+        import time
         K, M, N = self.K, self.M, self.N
         main = torch.cuda.current_stream()
         beta, betaZ = self.beta, self.betaZ
         acc_cur = None
+        t0 = time.perf_counter()
         for k in range(K - 1):                                                                   # 557-564
             self.noise_new[k].copy_(betaZ * self.noise_cur[k] + beta * self._sym(w_half[k]))
             if k == 0:
@@ -665,6 +667,7 @@ class DistPCN:
                 del Lk
         if acc_cur is None:                # two layers: no middle-layer solve to pair with
             phi_cur = self.phi.phi(self.L_cur)
+        t1 = time.perf_counter()                 # finalize() synchronised: phase 1 = middle-layer solves || Phi(L_current)
         L_latest = self.ctx.construct_L(self.u_new[K - 2], self.sqrt_betas[K - 1])               # 570
         # Gibbs right-hand sides of both accept outcomes (583-586): noise_cur[K-1] is read AFTER the accept copy
         sw = self._sym(w_last)
@@ -688,7 +691,8 @@ class DistPCN:
         self.u_new[K - 1].copy_(v_acc if accepted else v_rej)                                    # 598
         self.accepted_total += int(accepted)
         self.iteration += 1
-        self.last = dict(accepted=accepted, log_ratio=log_ratio, phi_cur=phi_cur, phi_new=phi_new, log_u=float(log_u))
+        self.last = dict(accepted=accepted, log_ratio=log_ratio, phi_cur=phi_cur, phi_new=phi_new, log_u=float(log_u),
+                         phase_s={"solves||phi_current": round(t1 - t0, 4), "gibbs_qr||phi_latest": round(time.perf_counter() - t1, 4)})
         return self.last
 
     def current_halves(self):
