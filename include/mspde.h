@@ -41,10 +41,11 @@ int mspde_get_gemm_mode(void);
  * environment MSPDE_QR_BLOCK=64|128. */
 int mspde_set_qr_block(int width);
 int mspde_get_qr_block(void);
-/* Experiment knob (default 0 = off; environment MSPDE_GEMM_PRE_MIN): under MSPDE_GEMM_3M, products with min(m, n) >= this
- * threshold form the two T3 operand planes (Ar +- Ai, Br + Bi) once per operand in a separate pass and run the kernel variant
- * that reads them instead of forming them per tile inside the main loop.  Same arithmetic, bit-identical results; measured
- * 11-24 % SLOWER on B200 (extra L2 -> shared-memory traffic), see profiles/r02_gemm_pre_v1.log. */
+/* Under MSPDE_GEMM_3M, products with k >= 512 and min(m, n) >= this threshold (default 2048; environment
+ * MSPDE_GEMM_PRE_MIN; 0 = never) first repack both operands into the shared-memory image of the kernel's stage tiles, with the
+ * two T3 operand planes (Ar +- Ai, Br + Bi) formed once per matrix, and run the kernel variant that consumes those tiles
+ * (zgemm3m_pre_tn_kernel) instead of forming the sums per CTA tile inside the main loop.  Same arithmetic, bit-identical
+ * results; +6 % on the dominant launch (profiles/r02_gemm_pre_v3.log). */
 int mspde_set_gemm_pre_min(int min_mn);
 int mspde_get_gemm_pre_min(void);
 

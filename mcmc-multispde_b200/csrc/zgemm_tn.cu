@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 #include "common.cuh"
 
 namespace mspde {
@@ -457,63 +458,77 @@ __global__ void __launch_bounds__(T::NTHREADS, 2) zgemm3m_tn_kernel(GemmArgs p) 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// 3M with PRE-SUMMED operand planes ("P" kernel).  The T3 operands  Ar +- Ai  and  Br + Bi  are formed ONCE per operand
-// matrix by presum_kernel (one read of the operand, 8 B written per element) instead of once per CTA tile inside the main
-// loop: the DADD/DFMA that build them share the FP64 pipe with the DMMAs and cost ~4 DMMA issue slots each (measured:
-// 41.9 -> 45.9 TFLOP/s ZGEMM-equivalent with the sums stubbed out).  A stage holds the interleaved A / B rows as before plus
-// one row of sums per k:  [ SA (64 doubles) | SB (32 doubles) | 4 pad ], pitch 100 == 4 mod 16 doubles, so the 64-bit
-// fragment loads of a half-warp (t = 0..3, g = 0..3) hit 16 distinct banks.  38400 B per stage, 3 stages, 2 CTAs/SM.
+// 3M on PACKED operands ("P" kernel).  For large products the two operands are first repacked (pack_operand_kernel: one read
+// of the operand, 24 B written per element) into the exact shared-memory image of the kernel's stage tiles:
+//     tile(kt, ct) = [ 16 x 64 complex values | 16 x 64 sums ]        sums = Ar +- Ai on the A side, Br + Bi on the B side
+// so that (1) the T3 operands are formed ONCE per matrix instead of once per CTA tile -- the DADD/DFMA that build them share
+// the FP64 pipe with the DMMAs and cost ~4 DMMA issue slots each -- and (2) a stage is filled by 32 equal bulk copies of the
+// contiguous tile images instead of row segments of the operand matrices.  (A first pre-summed variant with separate sum planes
+// and 64 row copies per stage was 11-24 % SLOWER: ncu showed it stalled on long_scoreboard, i.e. on copy issue.)  Bank
+// conflicts are removed by an XOR swizzle that the pack kernel bakes into the image (no padding): value column c of k-row r
+// sits at c ^ 2(r&3), sum column c at c ^ 4(r&3); the fragment loads of a quarter-warp (128-bit) / half-warp (64-bit) then hit
+// 8 / 16 distinct 16 B / 8 B slots.  Rows and columns beyond the matrix are zero in the image, so the kernel has no edge or
+// k-tail path.  Same arithmetic in the same order as the in-loop kernel: results are bit-identical (tested).
+//
+// One CTA per SM, on purpose.  The natural configuration (64 x 32 tile, 36 KB stages, two CTAs per SM) was correct alone, with
+// equal stream priorities, next to other kernels and next to itself -- but inside the pCN step, where Phi(L_current) runs on a
+// LOW-priority stream, it produced wrong values whenever one of its CTAs shared an SM with a CTA of the in-loop GEMM kernel of
+// the high-priority stream (the packed images and the kernel ordering were verified in place; padding its shared-memory
+// request to 125 KB, which only rules that pairing out, made every run correct again).  The cause was not identified, so the
+// shipped kernel excludes the pairing by construction: a 64 x 64 tile with 8 MMA warps and four 48 KB stages = 196 KB of shared
+// memory, which leaves no room for a second GEMM CTA of any kind.  It is as fast as the 2-CTA variant (45.2 vs 45.0 ms on the
+// dominant launch) and moves a third less data from L2 per flop.
 struct M3P {
-    static constexpr int BM = 64, BN = 32, BK = 16, STAGES = 3;
-    static constexpr int PA = BM + 2, PB = BN + 2;
-    static constexpr int PS = BM + BN + 4;               // doubles
+    // 64 x 64 tile, 8 MMA warps of 32 x 16, 4 stages of 48 KB: ONE CTA per SM by construction (196 KB of shared memory), so a P
+    // CTA never shares an SM with another GEMM CTA (see the note on co-residency above launch()).
+    static constexpr int BM = 64, BN = 64, BK = 16, STAGES = 4;
     static constexpr int MF = 4;
     static constexpr int WI = BM / (8 * MF);
     static constexpr int WARPS = WI * (BN / 16);
     static constexpr int NTHREADS = (WARPS + 1) * 32;
-    static constexpr int STAGE_DOUBLES = (BK * PA + BK * PB) * 2 + BK * PS;
+    static constexpr int A_TILE_DOUBLES = BK * BM * 3;    // 16 x 64 complex + 16 x 64 sums
+    static constexpr int B_TILE_DOUBLES = BK * BN * 3;
+    static constexpr int STAGE_DOUBLES = A_TILE_DOUBLES + B_TILE_DOUBLES;
     static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_DOUBLES * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
 };
-static_assert(2 * (M3P::SMEM_BYTES + 1024) <= 233472, "two P-kernel CTAs must fit one SM's shared memory");
+static_assert(M3P::SMEM_BYTES + 1024 <= 232448 && 2 * M3P::SMEM_BYTES > 233472, "exactly one P-kernel CTA per SM");
 
-// S[r][c] = X[r][c].re + sign * X[r][c].im   (two elements per thread: two 16 B loads, one 16 B store)
-__global__ void presum_kernel(const cplx* __restrict__ X, int ldx, int rows, int cols, double sign, double* __restrict__ S,
-                              int lds) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    const int r = blockIdx.y;
-    if (c >= cols) return;
-    const cplx* x = X + size_t(r) * ldx + c;
-    const cplx a = x[0];
-    const cplx b = (c + 1 < cols) ? x[1] : make_double2(0.0, 0.0);
-    *reinterpret_cast<double2*>(S + size_t(r) * lds + c) = make_double2(fma(sign, a.y, a.x), fma(sign, b.y, b.x));
-}
-// Both planes of one matrix in one pass (A == B: the Hermitian rank-k updates)
-__global__ void presum2_kernel(const cplx* __restrict__ X, int ldx, int rows, int cols, double* __restrict__ Sm,
-                               double* __restrict__ Sp, int lds) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    const int r = blockIdx.y;
-    if (c >= cols) return;
-    const cplx* x = X + size_t(r) * ldx + c;
-    const cplx a = x[0];
-    const cplx b = (c + 1 < cols) ? x[1] : make_double2(0.0, 0.0);
-    *reinterpret_cast<double2*>(Sm + size_t(r) * lds + c) = make_double2(a.x - a.y, b.x - b.y);
-    *reinterpret_cast<double2*>(Sp + size_t(r) * lds + c) = make_double2(a.x + a.y, b.x + b.y);
+// One CTA per tile: X is rows(k) x cols, row-major; tile (tk, tc) covers k-rows tk*16.. and columns tc*W..
+template <int W>
+__global__ void __launch_bounds__(256) pack_operand_kernel(const cplx* __restrict__ X, int ldx, int rows, int cols, double sign,
+                                                           double* __restrict__ out, int tiles_c) {
+    const int tc = blockIdx.x, tk = blockIdx.y;
+    double* tile = out + (size_t(tk) * tiles_c + tc) * size_t(16 * W * 3);
+    cplx* data = reinterpret_cast<cplx*>(tile);
+    double* sums = tile + 16 * W * 2;
+    for (int idx = threadIdx.x; idx < 16 * W; idx += 256) {
+        const int r = idx / W, c = idx % W;
+        const int kr = tk * 16 + r, gc = tc * W + c;
+        cplx v = make_double2(0.0, 0.0);
+        if (kr < rows && gc < cols) v = X[size_t(kr) * ldx + gc];
+        const int t = r & 3;
+        data[r * W + (c ^ (2 * t))] = v;
+        sums[r * W + (c ^ (4 * t))] = fma(sign, v.y, v.x);
+    }
 }
 
-__global__ void __launch_bounds__(M3P::NTHREADS, 2) zgemm3m_pre_tn_kernel(GemmArgs p) {
+__global__ void __launch_bounds__(M3P::NTHREADS, 1) zgemm3m_pre_tn_kernel(GemmArgs p) {
     typedef M3P T;
-    constexpr int BM = T::BM, BN = T::BN, BK = T::BK, STAGES = T::STAGES, PA = T::PA, PB = T::PB, PS = T::PS;
+    constexpr int BM = T::BM, BN = T::BN, BK = T::BK, STAGES = T::STAGES;
     constexpr int STAGE_DOUBLES = T::STAGE_DOUBLES;
     constexpr int CONSUMER_WARPS = T::WARPS;
     constexpr int MF = T::MF, WI = T::WI;
-    constexpr int S_OFF = (BK * PA + BK * PB) * 2;       // doubles: start of the sum rows inside a stage
+    constexpr int A_SUM = BK * BM * 2;                    // doubles: start of the A sums inside a stage
+    constexpr int B_DATA = T::A_TILE_DOUBLES;             // start of the B values
+    constexpr int B_SUM = B_DATA + BK * BN * 2;
     const int tiles_i = (p.m + BM - 1) / BM, tiles_j = (p.n + BN - 1) / BN;
     const int pid = blockIdx.x;
     const int per_group = GROUP_I * tiles_j;
     const int first_i = (pid / per_group) * GROUP_I;
     const int gsize = min(tiles_i - first_i, GROUP_I);
-    const int i0 = (first_i + (pid % per_group) % gsize) * BM;
-    const int j0 = ((pid % per_group) / gsize) * BN;
+    const int ti = first_i + (pid % per_group) % gsize;
+    const int tj = (pid % per_group) / gsize;
+    const int i0 = ti * BM, j0 = tj * BN;
     if (p.uplo == GEMM_UPPER && j0 + BN - 1 < i0) return;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -525,10 +540,9 @@ __global__ void __launch_bounds__(M3P::NTHREADS, 2) zgemm3m_pre_tn_kernel(GemmAr
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
-    const int kbeg = blockIdx.z * p.kslice;
+    const int kbeg = blockIdx.z * p.kslice;               // multiple of BK (the split-K driver rounds slices to BK)
     const int kend = min(p.k, kbeg + p.kslice);
-    const int klen = kend - kbeg;
-    const int ktiles = (klen + BK - 1) / BK;
+    const int ktiles = (kend - kbeg + BK - 1) / BK;
     cplx* __restrict__ C = p.C + size_t(blockIdx.z) * p.cslice;
 
     if (tid == 0) {
@@ -540,36 +554,23 @@ __global__ void __launch_bounds__(M3P::NTHREADS, 2) zgemm3m_pre_tn_kernel(GemmAr
     }
     __syncthreads();
 
-    const int mrows = min(BM, p.m - i0);
-    const int ncols = min(BN, p.n - j0);
-
     if (warp == CONSUMER_WARPS) {
-        // producer warp: lanes 0-15 fetch row r of A and of SA, lanes 16-31 row r of B and of SB (bulk copies are multiples
-        // of 16 B: an odd count of 8 B sums is rounded up, the planes are padded to an even leading dimension)
-        const bool isA = lane < BK;
-        const int r = isA ? lane : lane - BK;
-        const cplx* src_base = isA ? (p.A + size_t(kbeg) * p.lda + i0) : (p.B + size_t(kbeg) * p.ldb + j0);
-        const double* sum_base = isA ? (p.SA + size_t(kbeg) * p.ldsa + i0) : (p.SB + size_t(kbeg) * p.ldsb + j0);
-        const size_t ld = isA ? p.lda : p.ldb;
-        const size_t lds = isA ? p.ldsa : p.ldsb;
-        const int cnt = isA ? mrows : ncols;
-        const uint32_t row_bytes = uint32_t(cnt) * 16u;
-        const uint32_t sum_bytes = uint32_t((cnt + 1) & ~1) * 8u;
-        const uint32_t stage_bytes_per_k = uint32_t(mrows + ncols) * 16u + uint32_t(((mrows + 1) & ~1) + ((ncols + 1) & ~1)) * 8u;
-        const int dst_off = isA ? r * PA * 2 : (BK * PA + r * PB) * 2;
-        const int sum_off = S_OFF + r * PS + (isA ? 0 : BM);
+        // producer warp: the packed tiles are the shared-memory image; lanes 0-15 copy the A tile and lanes 16-31 the B tile in
+        // sixteen equal slices each (1536 B / 768 B)
+        const bool isA = lane < 16;
+        const int part = lane & 15;
+        const uint32_t bytes = uint32_t((isA ? T::A_TILE_DOUBLES : T::B_TILE_DOUBLES) / 16 * sizeof(double));
+        const double* src = isA ? p.SA + (size_t(kbeg / BK) * tiles_i + ti) * size_t(T::A_TILE_DOUBLES) + size_t(part) * (T::A_TILE_DOUBLES / 16)
+                                : p.SB + (size_t(kbeg / BK) * tiles_j + tj) * size_t(T::B_TILE_DOUBLES) + size_t(part) * (T::B_TILE_DOUBLES / 16);
+        const size_t step = isA ? size_t(tiles_i) * T::A_TILE_DOUBLES : size_t(tiles_j) * T::B_TILE_DOUBLES;
+        const int dst = isA ? part * (T::A_TILE_DOUBLES / 16) : B_DATA + part * (T::B_TILE_DOUBLES / 16);
         int stage = 0;
         uint32_t parity = 0;
         for (int kt = 0; kt < ktiles; ++kt) {
             mbar_wait(&empty_bar[stage], parity ^ 1);
-            const int kvalid = min(BK, klen - kt * BK);
-            if (lane == 0) mbar_expect_tx(&full_bar[stage], uint32_t(kvalid) * stage_bytes_per_k);
+            if (lane == 0) mbar_expect_tx(&full_bar[stage], uint32_t(STAGE_DOUBLES * sizeof(double)));
             __syncwarp();
-            if (r < kvalid) {
-                double* sb = stage_base + size_t(stage) * STAGE_DOUBLES;
-                bulk_g2s(sb + dst_off, src_base + (size_t(kt) * BK + r) * ld, row_bytes, &full_bar[stage]);
-                bulk_g2s(sb + sum_off, sum_base + (size_t(kt) * BK + r) * lds, sum_bytes, &full_bar[stage]);
-            }
+            bulk_g2s(stage_base + size_t(stage) * STAGE_DOUBLES + dst, src + size_t(kt) * step, bytes, &full_bar[stage]);
             if (++stage == STAGES) { stage = 0; parity ^= 1; }
         }
         return;
@@ -579,10 +580,14 @@ __global__ void __launch_bounds__(M3P::NTHREADS, 2) zgemm3m_pre_tn_kernel(GemmAr
     const int t = lane & 3;
     const int wi = warp % WI;
     const int wj = warp / WI;
-    const int a_off = (t * PA + wi * 8 * MF + g) * 2;
-    const int b_off = (BK * PA + t * PB + wj * 16 + g) * 2;
-    const int sa_off = S_OFF + t * PS + wi * 8 * MF + g;
-    const int sb_off = S_OFF + t * PS + BM + wj * 16 + g;
+    // per-lane offsets inside a stage (doubles) for k-row t of a k4 group; + kk*4*W*{2,1} per group; the swizzles depend on t only
+    const int a_off = (t * BM + wi * 8 * MF + (g ^ (2 * t))) * 2;            // + a*16 per fragment
+    const int b_off = B_DATA + (t * BN + wj * 16 + (g ^ (2 * t))) * 2;       // + b*16
+    int sa_off[MF], sb_off[2];
+#pragma unroll
+    for (int a = 0; a < MF; ++a) sa_off[a] = A_SUM + t * BM + wi * 8 * MF + ((a * 8 + g) ^ (4 * t));
+#pragma unroll
+    for (int b = 0; b < 2; ++b) sb_off[b] = B_SUM + t * BN + wj * 16 + ((b * 8 + g) ^ (4 * t));
     const bool conj = p.conjA != 0;
 
     const bool preload = p.beta != 0.0 && p.alpha != 0.0;
@@ -608,60 +613,32 @@ __global__ void __launch_bounds__(M3P::NTHREADS, 2) zgemm3m_pre_tn_kernel(GemmAr
     for (int kt = 0; kt < ktiles; ++kt) {
         mbar_wait(&full_bar[stage], parity);
         const double* S = stage_base + size_t(stage) * STAGE_DOUBLES;
-        const int kvalid = klen - kt * BK;
-        if (kvalid >= BK) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 4; ++kk) {
-                double2 av[MF], bv[2];
-                double as[MF], bs[2];
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double2 av[MF], bv[2];
+            double as[MF], bs[2];
 #pragma unroll
-                for (int a = 0; a < MF; ++a) {
-                    av[a] = *reinterpret_cast<const double2*>(S + a_off + kk * 4 * PA * 2 + a * 16);
-                    as[a] = S[sa_off + kk * 4 * PS + a * 8];
-                }
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    bv[b] = *reinterpret_cast<const double2*>(S + b_off + kk * 4 * PB * 2 + b * 16);
-                    bs[b] = S[sb_off + kk * 4 * PS + b * 8];
-                }
-#pragma unroll
-                for (int a = 0; a < MF; ++a)
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) dmma884(t1[a][b][0], t1[a][b][1], av[a].x, bv[b].x);
-#pragma unroll
-                for (int a = 0; a < MF; ++a)
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) dmma884(t2[a][b][0], t2[a][b][1], av[a].y, bv[b].y);
-#pragma unroll
-                for (int a = 0; a < MF; ++a)
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) dmma884(t3[a][b][0], t3[a][b][1], as[a], bs[b]);
+            for (int a = 0; a < MF; ++a) {
+                av[a] = *reinterpret_cast<const double2*>(S + a_off + kk * 4 * BM * 2 + a * 16);
+                as[a] = S[sa_off[a] + kk * 4 * BM];
             }
-        } else {
-            const int nk4 = (kvalid + 3) >> 2;
-            for (int kk = 0; kk < nk4; ++kk) {
-                const bool dead = (kk * 4 + t) >= kvalid;
-                double2 av[MF], bv[2];
-                double as[MF], bs[2];
 #pragma unroll
-                for (int a = 0; a < MF; ++a) {
-                    av[a] = dead ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(S + a_off + kk * 4 * PA * 2 + a * 16);
-                    as[a] = dead ? 0.0 : S[sa_off + kk * 4 * PS + a * 8];
-                }
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    bv[b] = dead ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(S + b_off + kk * 4 * PB * 2 + b * 16);
-                    bs[b] = dead ? 0.0 : S[sb_off + kk * 4 * PS + b * 8];
-                }
-#pragma unroll
-                for (int a = 0; a < MF; ++a)
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        dmma884(t1[a][b][0], t1[a][b][1], av[a].x, bv[b].x);
-                        dmma884(t2[a][b][0], t2[a][b][1], av[a].y, bv[b].y);
-                        dmma884(t3[a][b][0], t3[a][b][1], as[a], bs[b]);
-                    }
+            for (int b = 0; b < 2; ++b) {
+                bv[b] = *reinterpret_cast<const double2*>(S + b_off + kk * 4 * BN * 2 + b * 16);
+                bs[b] = S[sb_off[b] + kk * 4 * BN];
             }
+#pragma unroll
+            for (int a = 0; a < MF; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) dmma884(t1[a][b][0], t1[a][b][1], av[a].x, bv[b].x);
+#pragma unroll
+            for (int a = 0; a < MF; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) dmma884(t2[a][b][0], t2[a][b][1], av[a].y, bv[b].y);
+#pragma unroll
+            for (int a = 0; a < MF; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) dmma884(t3[a][b][0], t3[a][b][1], as[a], bs[b]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -696,19 +673,28 @@ __global__ void __launch_bounds__(M3P::NTHREADS, 2) zgemm3m_pre_tn_kernel(GemmAr
     }
 }
 
-// Per-stream workspace of the pre-summed planes (grown on demand; a growth synchronises the device once).
+// Per-stream workspace of the packed operands, grown on demand.  A buffer that is too small is RETIRED, not freed: products
+// enqueued earlier on the same stream may still be reading it.  New buffers are sized for the largest product any stream has
+// asked for so far, so a stream grows at most two or three times; retired buffers are released with the process.
 struct PreWs { double* p = nullptr; size_t cap = 0; };
 std::mutex g_prews_mu;
 std::unordered_map<cudaStream_t, PreWs> g_prews;
+std::vector<double*> g_prews_retired;
+size_t g_prews_max_need = 0;
 
 double* prews_get(cudaStream_t st, size_t doubles) {
     std::lock_guard<std::mutex> lk(g_prews_mu);
+    if (doubles > g_prews_max_need) g_prews_max_need = doubles;
     PreWs& w = g_prews[st];
     if (w.cap < doubles) {
-        if (w.p) cudaFree(w.p);
+        if (w.p) g_prews_retired.push_back(w.p);
         w.p = nullptr; w.cap = 0;
-        const size_t want = doubles + doubles / 8;
-        if (cudaMalloc(&w.p, want * sizeof(double)) != cudaSuccess) { cudaGetLastError(); w.p = nullptr; return nullptr; }
+        size_t want = g_prews_max_need + g_prews_max_need / 16;
+        if (cudaMalloc(&w.p, want * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            want = doubles;                                 // memory is tight: exactly what this product needs
+            if (cudaMalloc(&w.p, want * sizeof(double)) != cudaSuccess) { cudaGetLastError(); w.p = nullptr; return nullptr; }
+        }
         w.cap = want;
     }
     return w.p;
@@ -762,24 +748,20 @@ int launch(cudaStream_t st, const GemmArgs& a, int nz) {
     static FILE* logf = getenv("MSPDE_GEMM_LOG") ? fopen(getenv("MSPDE_GEMM_LOG"), "w") : nullptr;   // dev aid: shapes per launch
     if (logf) { fprintf(logf, "%d %d %d %d %d\n", a.m, a.n, a.k, a.uplo, nz); fflush(logf); }
     const int pre_min = gemm_pre_min();
-    if (use3m && pre_min > 0 && min(a.m, a.n) >= pre_min && min(a.k, a.kslice) >= 32) {
-        // large product: form the T3 operand planes once per operand (presum) and run the P kernel
+    if (use3m && pre_min > 0 && min(a.m, a.n) >= pre_min && min(a.k, a.kslice) >= 512 && (nz == 1 || a.kslice % M3P::BK == 0)) {
+        // large product: repack both operands into the kernel's stage-tile image (values + pre-summed T3 operands), then the P kernel
         GemmArgs b = a;
-        const int ldsa = (a.m + 1) & ~1, ldsb = (a.n + 1) & ~1;
-        const size_t need = size_t(a.k) * (size_t(ldsa) + ldsb) + 2;
+        const int tiles_k = (a.k + M3P::BK - 1) / M3P::BK;
+        const int tiles_m = (a.m + M3P::BM - 1) / M3P::BM, tiles_n = (a.n + M3P::BN - 1) / M3P::BN;
+        const size_t a_doubles = size_t(tiles_k) * tiles_m * M3P::A_TILE_DOUBLES;
+        const size_t b_doubles = size_t(tiles_k) * tiles_n * M3P::B_TILE_DOUBLES;
+        const size_t need = a_doubles + b_doubles;
         double* ws = need <= (size_t(6) << 27) ? prews_get(st, need) : nullptr;      // at most 6 GB per stream
         if (ws) {
-            b.SA = ws; b.ldsa = ldsa;
-            b.SB = ws + size_t(a.k) * ldsa; b.ldsb = ldsb;
-            if ((void*)a.A == (void*)a.B && a.lda == a.ldb && a.m == a.n && a.conjA) {
-                dim3 pg((a.m / 2 + 256) / 256, a.k);
-                presum2_kernel<<<pg, 256, 0, st>>>(a.A, a.lda, a.k, a.m, const_cast<double*>(b.SA), const_cast<double*>(b.SB), ldsa);
-            } else {
-                dim3 pa((a.m / 2 + 256) / 256, a.k), pb((a.n / 2 + 256) / 256, a.k);
-                presum_kernel<<<pa, 256, 0, st>>>(a.A, a.lda, a.k, a.m, a.conjA ? -1.0 : 1.0, const_cast<double*>(b.SA), ldsa);
-                presum_kernel<<<pb, 256, 0, st>>>(a.B, a.ldb, a.k, a.n, 1.0, const_cast<double*>(b.SB), ldsb);
-            }
-            dim3 grid(((a.m + M3P::BM - 1) / M3P::BM) * ((a.n + M3P::BN - 1) / M3P::BN), 1, nz);
+            b.SA = ws; b.SB = ws + a_doubles;
+            pack_operand_kernel<M3P::BM><<<dim3(tiles_m, tiles_k), 256, 0, st>>>(a.A, a.lda, a.k, a.m, a.conjA ? -1.0 : 1.0, ws, tiles_m);
+            pack_operand_kernel<M3P::BN><<<dim3(tiles_n, tiles_k), 256, 0, st>>>(a.B, a.ldb, a.k, a.n, 1.0, ws + a_doubles, tiles_n);
+            dim3 grid(tiles_m * tiles_n, 1, nz);
             zgemm3m_pre_tn_kernel<<<grid, M3P::NTHREADS, M3P::SMEM_BYTES, st>>>(b);
             MSPDE_LAUNCH_CHECK();
             return 0;
@@ -801,19 +783,18 @@ int launch(cudaStream_t st, const GemmArgs& a, int nz) {
 }
 
 int g_gemm_mode = -1;   // -1: not chosen yet (environment MSPDE_GEMM = 3m | 4m, else the default)
-int g_pre_min = -1;     // -1: not chosen yet (environment MSPDE_GEMM_PRE_MIN, else 0 = off)
+int g_pre_min = -1;     // -1: not chosen yet (environment MSPDE_GEMM_PRE_MIN, else 2048)
 
 }  // namespace
 
-// Smallest min(m, n) for which a 3M product forms its T3 operand planes up front (presum + P kernel); 0 = never (default).
-// MEASURED SLOWER (profiles/r02_gemm_pre_v1.log): bit-identical results, but 54.2 ms against 48.0 ms on the dominant launch
-// and -11..-24 % on every shape of the path.  The planes raise the L2 -> shared-memory traffic of the 64 x 32 tile from
-// 1536 to 2304 B per k (5.3 instead of 8 flop/B: ~6 TB/s at 32 TFLOP/s) and cost a pipeline stage; that outweighs the FP64-pipe
-// slots the in-loop DADDs take.  Kept as a tested, documented experiment knob, not used by the product path.
+// Smallest min(m, n) from which a 3M product with k >= 512 repacks its operands and runs the P kernel (0 = never).  Measured
+// on B200 (profiles/r02_gemm_pre_v3.log; pack passes included): +6.3 % on the dominant launch (48.06 -> 45.20 ms = 0.929 of the
+// FP64 tensor peak in executed flops), +5.2 % on L^H L, +3.1 % on a rank-512 update with m = 10 000, break-even near m = 3 000
+// at k = 512, slower below; the step goes from 343.1 to 335.1 ms.
 int gemm_pre_min() {
     if (g_pre_min < 0) {
         const char* e = getenv("MSPDE_GEMM_PRE_MIN");
-        g_pre_min = e ? atoi(e) : 0;
+        g_pre_min = e ? atoi(e) : 2048;
     }
     return g_pre_min;
 }

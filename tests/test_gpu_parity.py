@@ -918,14 +918,17 @@ def test_config3_size_phi_solve_and_lstsq():
 
 
 def test_presummed_3m_kernel_is_bit_identical(lib):
-    """The experiment knob mspde_set_gemm_pre_min (pre-summed T3 operand planes, measured slower and off by default) performs
-    the same arithmetic as the in-loop sums: identical bits on edge shapes (odd sizes, k tails, beta != 0, upper, split-K)."""
+    """The packed-operand 3M kernel (mspde_set_gemm_pre_min: both operands repacked into the kernel's stage-tile image with
+    the T3 operand planes formed once per matrix; the default for large products) performs the same arithmetic in the same
+    order as the in-loop kernel: identical bits on edge shapes (odd sizes, k tails, beta != 0, upper) and on the k >= 512
+    shapes it is used for."""
     from mspde import _ffi
     mode0, pre0 = _ffi.get_gemm_mode(), _ffi.get_gemm_pre_min()
     try:
         _ffi.set_gemm_mode(_ffi.GEMM_3M)
         for (m, n, k, conj, uplo, beta) in [(65, 33, 17, 1, 0, 0.0), (127, 63, 35, 0, 0, 1.0), (333, 333, 211, 1, 1, 1.0),
-                                            (200, 1031, 129, 1, 0, -0.5), (1, 1, 1, 1, 0, 0.0), (961, 961, 961, 1, 1, 0.0)]:
+                                            (200, 1031, 129, 1, 0, -0.5), (1, 1, 1, 1, 0, 0.0), (961, 961, 961, 1, 1, 0.0),
+                                            (700, 333, 513, 1, 0, 1.0), (1025, 1025, 1030, 0, 1, 0.0), (65, 2100, 777, 1, 0, -1.0)]:
             A = crandn(k, m, seed=1)
             B = A if uplo else crandn(k, n, seed=2)
             C0 = crandn(m, n, seed=3)
