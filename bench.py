@@ -650,7 +650,18 @@ def main():
         ach = fl / (ms_k * 1e-3) / 1e12
         step_rate = f_iter / (ms_dev * 1e-3 / args.steps) / 1e12
         scheme = "3M: three real DMMA products per complex product" if gemm_mode == _ffi.GEMM_3M else "4M: four real DMMA products"
-        kname = "zgemm3m_tn_kernel" if gemm_mode == _ffi.GEMM_3M else "zgemm_tn_kernel"
+        packed = gemm_mode == _ffi.GEMM_3M and 0 < _ffi.get_gemm_pre_min() <= min(M, N)
+        kname = ("zgemm3m_pre_tn_kernel + 2 x pack_operand_kernel (operands repacked into the stage-tile image, T3 planes pre-summed)"
+                 if packed else ("zgemm3m_tn_kernel" if gemm_mode == _ffi.GEMM_3M else "zgemm_tn_kernel"))
+        if packed:
+            traffic, traffic_src = 23.6e9, ("profiles/r02_zgemm3m_packed_full.ncu-rep: zgemm3m_pre_tn_kernel 19.00e9 read + 1.04e9 written "
+                                            "(44.60 ms, tensor pipe 95.5 % active, L2 hit 79.9 %) + two pack passes of 0.73e9 read + 1.04e9 "
+                                            "written each (0.27 ms each); algorithmic 0.73e9 + 1.05e9; DRAM runs at ~6 % of its peak")
+        elif gemm_mode == _ffi.GEMM_3M:
+            traffic, traffic_src = 15.44e9, ("profiles/r02_zgemm3m_full.ncu-rep (in-loop sums: 14.40e9 read + 1.05e9 written, tensor pipe "
+                                             "88.6 % active, L2 hit 85.5 %)")
+        else:
+            traffic, traffic_src = 13.1e9, "profiles/r01_zgemm_full_v2.ncu-rep (grouped tile rasterisation; 56.2e9 before it)"
         roofline = {"kernel": "%s (DMMA m8n8k4, %s), launch Q_inv = I - Ht^H Ht, upper triangle, m=n=%d k=%d" % (kname, scheme, M, N),
                     "bound": "tensor", "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
                     "flops_per_launch": fl, "zgemm_equivalent": {"flops_per_launch": fl8, "achieved": fl8 / (ms_k * 1e-3) / 1e12,
@@ -658,13 +669,9 @@ def main():
                                                                  "note": "same launch counted at 8 flop per complex multiply-add (SURVEY 8d's "
                                                                          "ZHERK = 4 n^2 k), the convention ZGEMM rates are quoted in; above 1.0 "
                                                                          "under 3M because the kernel's algorithm needs 6"},
-                    "traffic": 15.44e9 if gemm_mode == _ffi.GEMM_3M else 13.1e9,
-                    "traffic_source": "dram__bytes_read+write of this launch from one ncu --set full capture: "
-                                      + ("profiles/r02_zgemm3m_full.ncu-rep (14.40e9 read + 1.05e9 written; algorithmic 0.73e9 + 1.05e9: "
-                                         "operand panels are re-read from DRAM when a wave's working set leaves the L2, 85.5 % L2 hit rate; "
-                                         "DRAM runs at ~4 % of its peak, the tensor pipe at 88.6 % active)"
-                                         if gemm_mode == _ffi.GEMM_3M else
-                                         "profiles/r01_zgemm_full_v2.ncu-rep (grouped tile rasterisation; 56.2e9 before it)"),
+                    "traffic": traffic,
+                    "traffic_source": "dram__bytes_read+write of this launch from one ncu --set full capture: " + traffic_src,
+                    "timing_note": "ms_per_launch is the whole mspde_zgemm_tn call (pack passes included when the packed kernel is used)",
                     "ms_per_launch": ms_k,
                     "peak_source": fp64_peak_source,
                     "step_fp64": {"flops_per_step": f_iter, "achieved": step_rate, "frac": step_rate / FP64_PEAK_TFLOPS,
