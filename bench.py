@@ -16,6 +16,7 @@ all_gather of the recorded samples inside the timed region; scaling is weak.
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import math
 import os
@@ -248,6 +249,47 @@ def config5_block(cfg, dev, rank, world, steps, warmup, fp64_peak, selfcheck_n=(
     out = {"config": {"workload": f"BASELINE configs[4]: 3 layers, n={cfg['n']} (N={N}, M={M}), single chain, every factorization "
                                   "block-distributed over NCCL/NVLink (mspde.dist.DistPCN: state, injected noise, accept on the "
                                   "all-reduced Phi values, Gibbs draw with both outcomes' right-hand sides)"}}
+    # (0) every rank must enter or skip together: a rank that runs out of memory mid-factorization leaves the others waiting in
+    # a broadcast.  Give back what earlier phases of this process kept, then agree on the smallest free HBM of any rank.
+    torch.cuda.synchronize()
+    _ffi.release_gemm_workspaces()
+    torch.cuda.empty_cache()
+    need = config5_bytes_per_rank(N, M, world)
+    free = torch.tensor([float(torch.cuda.mem_get_info(dev)[0])], dtype=torch.float64, device=dev)
+    dist.all_reduce(free, op=dist.ReduceOp.MIN)
+    out["hbm"] = {"needed_bytes_per_rank_estimate": need, "min_free_bytes_over_ranks": float(free.item())}
+    if float(free.item()) < need:
+        out["unavailable"] = (f"needs about {need / 2**30:.0f} GiB of free HBM on every rank, the fullest rank has "
+                              f"{float(free.item()) / 2**30:.0f} GiB: skipped on all ranks")
+        return out
+    # The distributed sampler's numbers were taken with the in-loop 3M kernel (profiles/r02_bench_8gpu_b.json); its per-rank
+    # panel updates are short-k products the packed kernel does not help, and the packed operands' workspaces are HBM this
+    # configuration needs.  Process-wide switch, restored on the way out.
+    pre_min0 = _ffi.get_gemm_pre_min()
+    _ffi.set_gemm_pre_min(0)
+    try:
+        return _config5_measure(out, cfg, dev, rank, world, steps, warmup, fp64_peak, selfcheck_n, local_rank, f_iter, N, M)
+    finally:
+        _ffi.set_gemm_pre_min(pre_min0)
+        torch.cuda.empty_cache()
+
+
+def config5_bytes_per_rank(N, M, world):
+    """Free HBM a rank needs for the n=96 distributed step: the peak seen by torch's allocator on 8 B200 was 126.5 GiB at
+    N=36481, M=17190 (profiles/r02_bench_8gpu_c.json's out-of-memory report: 106.7 GiB live + a 19.8 GiB request), which is
+    1.25 x the (M+N) x (M+N) augmented Gibbs matrix + 4 N x N + 2 M x N complex128 blocks a rank holds when world=8; scaled
+    with the same expression, plus 15 % for allocator fragmentation."""
+    blocks = 16.0 * ((M + N) ** 2 + 4.0 * N * N + 2.0 * M * N)
+    at8 = 16.0 * ((17190 + 36481) ** 2 + 4.0 * 36481 ** 2 + 2.0 * 17190 * 36481)
+    return 1.15 * 126.5 * 2**30 * (blocks / at8) * (8.0 / world) ** 0.5
+
+
+def _config5_measure(out, cfg, dev, rank, world, steps, warmup, fp64_peak, selfcheck_n, local_rank, f_iter, N, M):
+    import torch
+    import torch.distributed as dist
+    from mspde import _ffi
+    from mspde.dist import build_dist_chain
+    import dist_chain_check as dcc
     # (1) correctness evidence recorded with the number: distributed sampler == single-GPU kernels on the same inputs
     out["selfcheck_vs_single_gpu"] = [dcc.single_vs_dist(n, dev, rank) for n in selfcheck_n]
     torch.cuda.empty_cache()
@@ -432,7 +474,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # a rank lost mid-collective should end the run in minutes, not after NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     f_iter, N, M = flops_iter(**cfg)
     FP64_PEAK_TFLOPS, fp64_peak_source = measure_fp64_peak(_ffi)
     if args.config == 5:
@@ -444,8 +487,8 @@ def main():
         blk = config5_block(cfg, dev, rank, world, steps=args.steps, warmup=min(args.warmup, 1), fp64_peak=FP64_PEAK_TFLOPS,
                             selfcheck_n=(32,), local_rank=local_rank)
         if rank == 0:
-            line = {"metric": "pCN iters/sec (n=96, 3 layers, one chain block-distributed)", "value": blk["value"], "unit": "iters/s",
-                    "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": blk["ms_per_step"],
+            line = {"metric": "pCN iters/sec (n=96, 3 layers, one chain block-distributed)", "value": blk.get("value"), "unit": "iters/s",
+                    "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": blk.get("ms_per_step"),
                     "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
             line.update({k: v for k, v in blk.items() if k not in ("value", "ms_per_step")})
             emit(line)
@@ -732,6 +775,7 @@ def main():
         # the two multi-GPU splits north_star names, measured in the same driver-visible run
         sim.pcn.ctx.close()
         del sim, pcn, ctx, Layers, cb, dev_noise, rec, outs
+        _ffi.release_gemm_workspaces()
         torch.cuda.empty_cache()
         try:
             config4 = config4_block(cfg, dev, rank, world, local_rank)

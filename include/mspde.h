@@ -48,6 +48,10 @@ int mspde_get_qr_block(void);
  * results; +6 % on the dominant launch (profiles/r02_gemm_pre_v3.log). */
 int mspde_set_gemm_pre_min(int min_mn);
 int mspde_get_gemm_pre_min(void);
+/* The repacked operands live in one workspace per stream, grown on demand and kept for the stream's next product; a context
+ * returns its own streams' workspaces in mspde_ctx_destroy.  This call waits for the device and frees all of them (those of
+ * caller-provided streams included); returns the bytes given back.  Use it before a phase that needs the whole HBM. */
+long long mspde_release_gemm_workspaces(void);
 
 /* Context = sizes + borrowed fixed inputs + library-owned workspace (replaces the managed-memory pool and the
  * temporaries of pCN._log_ratio, mcmc/image_cupy.py:834-835, 634-643). */

@@ -50,6 +50,7 @@ int mspde_set_qr_block(int k) { return set_qr_block_width(k); }
 int mspde_get_qr_block(void) { return qr_block_width(); }
 int mspde_set_gemm_pre_min(int v) { return set_gemm_pre_min(v); }
 int mspde_get_gemm_pre_min(void) { return gemm_pre_min(); }
+long long mspde_release_gemm_workspaces(void) { return (long long)gemm_release_all(); }
 
 int mspde_ctx_create(mspde_ctx** out, int device, int n, int n_ext, int M, int n_layers, void* stream) {
     return mspde_ctx_create_ex(out, device, n, n_ext, M, n_layers, stream, 0);
@@ -161,6 +162,8 @@ int mspde_ctx_create_ex(mspde_ctx** out, int device, int n, int n_ext, int M, in
 
 int mspde_ctx_destroy(mspde_ctx* h) {
     if (!h) return 0;
+    for (cudaStream_t q : {h->c.s0, h->c.s1, h->c.s2, h->c.qr_la.aux, h->c.pw[0].la.aux, h->c.pw[1].la.aux})
+        if (q) gemm_release_stream(q);              // packed-operand workspaces these streams own (zgemm_tn.cu)
     if (h->c.s0) cudaStreamDestroy(h->c.s0);
     if (h->c.ev_out) cudaEventDestroy(h->c.ev_out);
     if (h->c.s1) cudaStreamDestroy(h->c.s1);

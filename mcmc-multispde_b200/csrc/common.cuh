@@ -92,6 +92,8 @@ int gemm_mode();
 int set_gemm_mode(int mode);
 int gemm_pre_min();
 int set_gemm_pre_min(int v);
+void gemm_release_stream(cudaStream_t st);   // packed-operand workspace of one stream (before the stream is destroyed)
+size_t gemm_release_all();                    // every packed-operand workspace; waits for the device
 // C[i][j] = alpha * sum_k opA(A[k][i]) * B[k][j] + beta * C[i][j];  A: k x m, B: k x n, C: m x n, row-major.
 int zgemm_tn(cudaStream_t st, bool conjA, int m, int n, int k, double alpha, const cplx* A, int lda,
              const cplx* B, int ldb, double beta, cplx* C, int ldc, int uplo);

@@ -675,7 +675,8 @@ __global__ void __launch_bounds__(M3P::NTHREADS, 1) zgemm3m_pre_tn_kernel(GemmAr
 
 // Per-stream workspace of the packed operands, grown on demand.  A buffer that is too small is RETIRED, not freed: products
 // enqueued earlier on the same stream may still be reading it.  New buffers are sized for the largest product any stream has
-// asked for so far, so a stream grows at most two or three times; retired buffers are released with the process.
+// asked for so far, so a stream grows at most two or three times.  A context hands its streams' buffers back when it is
+// destroyed (gemm_release_stream); gemm_release_all frees everything, the retired buffers included, once the device is idle.
 struct PreWs { double* p = nullptr; size_t cap = 0; };
 std::mutex g_prews_mu;
 std::unordered_map<cudaStream_t, PreWs> g_prews;
@@ -801,6 +802,32 @@ int gemm_pre_min() {
 int set_gemm_pre_min(int v) {
     g_pre_min = v < 0 ? 0 : v;
     return 0;
+}
+
+// Frees the packed-operand workspace a stream owns.  The caller is about to destroy the stream: its queued work is waited for.
+void gemm_release_stream(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prews_mu);
+    auto it = g_prews.find(st);
+    if (it == g_prews.end()) return;
+    cudaStreamSynchronize(st);
+    if (it->second.p) cudaFree(it->second.p);
+    g_prews.erase(it);
+}
+
+// Frees every packed-operand workspace of the process (live and retired) after waiting for the device; the next large
+// product allocates afresh.  Returns the number of bytes given back.
+size_t gemm_release_all() {
+    std::lock_guard<std::mutex> lk(g_prews_mu);
+    cudaDeviceSynchronize();
+    size_t bytes = 0;
+    for (auto& kv : g_prews)
+        if (kv.second.p) { cudaFree(kv.second.p); bytes += kv.second.cap * sizeof(double); }
+    g_prews.clear();
+    for (double* p : g_prews_retired) cudaFree(p);
+    g_prews_retired.clear();
+    g_prews_max_need = 0;
+    cudaGetLastError();
+    return bytes;
 }
 
 int gemm_mode() {

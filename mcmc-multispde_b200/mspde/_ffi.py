@@ -74,6 +74,13 @@ def get_gemm_pre_min() -> int:
     return int(lib().mspde_get_gemm_pre_min())
 
 
+def release_gemm_workspaces() -> int:
+    """Waits for the device and frees every packed-operand workspace the GEMM kept (include/mspde.h); returns the bytes freed."""
+    L = lib()
+    L.mspde_release_gemm_workspaces.restype = ctypes.c_longlong
+    return int(L.mspde_release_gemm_workspaces())
+
+
 def set_qr_block(width: int):
     """64 or 128: block-reflector width of the Householder QR (include/mspde.h: mspde_set_qr_block)."""
     check(lib().mspde_set_qr_block(int(width)), "set_qr_block")
