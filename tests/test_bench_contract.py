@@ -44,3 +44,14 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_config5_memory_guard_is_calibrated_on_the_observed_peak():
+    """bench.config5_bytes_per_rank: the collective free-HBM check before the n=96 block.  At the measured point (8 ranks) it
+    asks for the observed allocator peak plus fragmentation headroom and stays below what a B200 has free; fewer ranks need
+    more per rank, a smaller basis less."""
+    import bench
+    at8 = bench.config5_bytes_per_rank(36481, 17190, 8)
+    assert 126.5 * 2**30 < at8 < 165 * 2**30
+    assert bench.config5_bytes_per_rank(36481, 17190, 4) > at8 > bench.config5_bytes_per_rank(36481, 17190, 16)
+    assert bench.config5_bytes_per_rank(16129, 11430, 8) < 0.3 * at8

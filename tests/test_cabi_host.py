@@ -77,3 +77,28 @@ def test_gemm_mode_switch_is_host_only():
         assert _ffi.get_gemm_mode() == _ffi.GEMM_4M
     finally:
         _ffi.set_gemm_mode(default)
+
+
+def test_process_wide_knobs_are_host_only():
+    """mspde_set/get_gemm_pre_min, mspde_set/get_qr_block and mspde_release_gemm_workspaces (include/mspde.h) work without a
+    device: the threshold round-trips (negative values clamp to 0 = never), the block width accepts 64 and 128 only, and
+    releasing when nothing was ever allocated returns 0 bytes."""
+    pre0, qr0 = _ffi.get_gemm_pre_min(), _ffi.get_qr_block()
+    try:
+        if not os.environ.get("MSPDE_GEMM_PRE_MIN"):
+            assert pre0 == 2048
+        _ffi.set_gemm_pre_min(0)
+        assert _ffi.get_gemm_pre_min() == 0
+        _ffi.set_gemm_pre_min(-5)
+        assert _ffi.get_gemm_pre_min() == 0
+        _ffi.set_gemm_pre_min(4096)
+        assert _ffi.get_gemm_pre_min() == 4096
+        for w in (64, 128):
+            _ffi.set_qr_block(w)
+            assert _ffi.get_qr_block() == w
+        with pytest.raises(_ffi.MspdeError):
+            _ffi.set_qr_block(96)
+        assert _ffi.release_gemm_workspaces() == 0
+    finally:
+        _ffi.set_gemm_pre_min(pre0)
+        _ffi.set_qr_block(qr0)
