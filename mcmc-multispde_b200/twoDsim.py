@@ -23,7 +23,11 @@ class _TriStateFlag(argparse.Action):
         super().__init__(option_strings, dest, nargs="?", default=default, help=help)
 
     def __call__(self, parser, namespace, values, option_string=None):
-        if option_string.startswith("--no"):
+        seen = namespace.__dict__.setdefault("_flag_spellings", {})
+        negated = option_string.startswith("--no")
+        if seen.setdefault(self.dest, negated) != negated:      # the two spellings exclude each other, as in the reference
+            parser.error(f"argument {option_string}: not allowed with the opposite spelling of the same flag")
+        if negated:
             if values is not None:
                 parser.error(f"{option_string} takes no value")
             setattr(namespace, self.dest, False)
@@ -38,7 +42,8 @@ def add_boolean_argument(parser, name, default=False, messages=""):
     parser.add_argument("--" + name, "--no" + name, dest=name.replace("-", "_"), action=_TriStateFlag, default=default, help=messages)
 
 
-def main(argv=None):
+def build_parser():
+    """The reference driver's option schema (twoDsim.py:68-95): same names, types and defaults."""
     parser = argparse.ArgumentParser()
     parser.add_argument('--iter', default=0, type=int)
     parser.add_argument('--seq-no', default=0, type=int)
@@ -68,9 +73,19 @@ def main(argv=None):
     add_boolean_argument(parser, 'verbose', default=True)
     add_boolean_argument(parser, 'hybrid', default=False)
     add_boolean_argument(parser, 'adapt-sqrtbeta', default=False)
-    args = parser.parse_args(argv)
+    return parser
+
+
+def parse_args(argv=None):
+    args = build_parser().parse_args(argv)
+    args.__dict__.pop("_flag_spellings", None)
     if args.n_theta == 18:                      # twoDsim.py:98-99
         args.seed = 2
+    return args
+
+
+def main(argv=None):
+    args = parse_args(argv)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     sim = im.Simulation(n_layers=args.n_layers, n_samples=args.n_samples, n=args.n, n_extended=args.n_extended, beta=args.beta,
                         kappa=args.kappa, sigma_0=args.sigma_0, sigma_v=args.sigma_v, sigma_scaling=args.sigma_scaling,
