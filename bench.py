@@ -51,6 +51,41 @@ def flops_iter(n, n_ext, n_theta, n_layers):
     return (n_layers - 2) * 8 / 3 * N ** 3 + 2 * f_phi + f_qr, N, M
 
 
+_GUARD_CHILD = r"""
+import sys
+fallback = sys.stdin.readline()
+rest = sys.stdin.read()                 # returns when the parent closes the pipe -- or dies
+if "DISARM" not in rest and fallback.strip():
+    sys.stdout.write(fallback if fallback.endswith("\n") else fallback + "\n")
+    sys.stdout.flush()
+"""
+
+
+class LineGuard:
+    """Insurance for the one JSON line while rank 0 is inside a collective phase that another rank can stall: a small child
+    process holds a complete fallback line (everything measured so far) and prints it to the result descriptor if this process
+    ends without disarming it -- e.g. killed by NCCL's watchdog.  disarm() is called on every normal path, so stdout still
+    carries exactly one line."""
+
+    def __init__(self, fallback_line):
+        out = _RESULT_FD if _RESULT_FD is not None else 1
+        sys.stdout.flush()
+        self.proc = subprocess.Popen([sys.executable, "-c", _GUARD_CHILD], stdin=subprocess.PIPE, stdout=out, close_fds=True)
+        self.proc.stdin.write((json.dumps(fallback_line) + "\n").encode())
+        self.proc.stdin.flush()
+
+    def disarm(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.stdin.write(b"DISARM\n")
+            self.proc.stdin.close()
+            self.proc.wait(timeout=30)
+        except Exception as ex:                                   # never lose the real line to the insurance
+            sys.stderr.write(f"line guard: {ex!r}\n")
+        self.proc = None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
@@ -770,25 +805,7 @@ def main():
         rate, desc, cores, dt, done = cpu_oracle_rate(cfg, steps=1, warmup=0, budget_s=30.0)
         cpu_baseline = {"value": rate, "unit": "iters/s", "cores": cores, "kind": "port", "sample": desc}
 
-    config4 = config5 = None
-    if world > 1 and args.config == 2 and not args.no_extras:
-        # the two multi-GPU splits north_star names, measured in the same driver-visible run (SURVEY 8e)
-        sim.pcn.ctx.close()
-        del sim, pcn, ctx, Layers, cb, dev_noise, rec, outs
-        _ffi.release_gemm_workspaces()
-        torch.cuda.empty_cache()
-        try:
-            config4 = config4_block(cfg, dev, rank, world, local_rank)
-        except Exception as ex:                     # keep the headline line even if an extra block fails
-            config4 = {"unavailable": repr(ex)[:300]}
-        if world >= 8 or args.with_config5:
-            try:
-                config5 = config5_block(CONFIGS[5], dev, rank, world, steps=2, warmup=1, fp64_peak=FP64_PEAK_TFLOPS,
-                                        selfcheck_n=(32,), local_rank=local_rank)
-            except Exception as ex:
-                config5 = {"unavailable": repr(ex)[:300]}
-
-    if rank == 0:
+    def headline(config4, config5):
         line = {"metric": f"pCN iters/sec (n={cfg['n']}, {cfg['n_layers']} layers)", "value": value, "unit": "iters/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -798,7 +815,38 @@ def main():
                 "library_standin": library, "config4_64_chains": config4, "config5_n96_distributed": config5,
                 "gemm_scheme": "3m" if gemm_mode == _ffi.GEMM_3M else "4m", "acceptance_rate": acc_rate, "setup_s": t_setup}
         line.update(extra)
-        emit(line)
+        return line
+
+    config4 = config5 = None
+    if world > 1 and args.config == 2 and not args.no_extras:
+        # the two multi-GPU splits north_star names, measured in the same driver-visible run (SURVEY 8e)
+        sim.pcn.ctx.close()
+        del sim, pcn, ctx, Layers, cb, dev_noise, rec, outs
+        _ffi.release_gemm_workspaces()
+        torch.cuda.empty_cache()
+        lost = {"unavailable": "rank 0 did not return from this block (another rank stalled or failed); the rest of the line was "
+                               "measured before it started"}
+        guard = LineGuard(headline(dict(lost), dict(lost))) if rank == 0 else None
+        try:
+            try:
+                config4 = config4_block(cfg, dev, rank, world, local_rank)
+            except Exception as ex:                     # keep the headline line even if an extra block fails
+                config4 = {"unavailable": repr(ex)[:300]}
+            if world >= 8 or args.with_config5:
+                if guard is not None:
+                    guard.disarm()
+                    guard = LineGuard(headline(config4, dict(lost)))
+                try:
+                    config5 = config5_block(CONFIGS[5], dev, rank, world, steps=2, warmup=1, fp64_peak=FP64_PEAK_TFLOPS,
+                                            selfcheck_n=(32,), local_rank=local_rank)
+                except Exception as ex:
+                    config5 = {"unavailable": repr(ex)[:300]}
+        finally:
+            if guard is not None:
+                guard.disarm()
+
+    if rank == 0:
+        emit(headline(config4, config5))
     if world > 1:
         dist.destroy_process_group()
 

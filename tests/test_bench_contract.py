@@ -55,3 +55,22 @@ def test_config5_memory_guard_is_calibrated_on_the_observed_peak():
     assert 126.5 * 2**30 < at8 < 165 * 2**30
     assert bench.config5_bytes_per_rank(36481, 17190, 4) > at8 > bench.config5_bytes_per_rank(36481, 17190, 16)
     assert bench.config5_bytes_per_rank(16129, 11430, 8) < 0.3 * at8
+
+
+def _run_guard_script(body):
+    code = ("import os, sys, json\nsys.path.insert(0, %r)\nimport bench\nbench.reserve_stdout()\n"
+            "g = bench.LineGuard({'metric': 'm', 'value': 1.5})\n" % ROOT) + body
+    return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+
+
+def test_line_guard_prints_the_fallback_when_the_process_dies():
+    """bench.LineGuard: if rank 0 is killed inside a collective block (NCCL watchdog abort), the fallback line still reaches the
+    result descriptor; on the normal path (disarm, then emit) stdout carries exactly the one real line."""
+    died = _run_guard_script("os.abort()\n")
+    assert died.returncode != 0
+    lines = [l for l in died.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0]) == {"metric": "m", "value": 1.5}
+    ok = _run_guard_script("g.disarm()\nbench.emit({'metric': 'm', 'value': 2.5})\n")
+    assert ok.returncode == 0, ok.stderr
+    lines = [l for l in ok.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["value"] == 2.5
