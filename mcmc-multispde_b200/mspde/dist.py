@@ -740,3 +740,136 @@ def build_dist_chain(n, n_ext, n_theta, n_layers, device, seed=7, beta=0.3, meas
         return w, log_u, w_half(), torch.as_tensor(rng.standard_normal(M)).to(device)
     chain.init_from_prior(lambda: chain._sym(w_half()))
     return chain, noise_fn
+
+
+class _HistoryLayer:
+    """What Simulation.run / the result file need from a Layer (image_cupy.py:717-807) when the state lives in a DistPCN."""
+
+    def __init__(self, order_number, sqrt_beta, history_length, nr):
+        import numpy as np
+        self.order_number = order_number
+        self.is_stationary = order_number == 0
+        self.sqrt_beta = float(sqrt_beta)
+        self.samples_history = np.empty((history_length, nr), dtype=np.complex128)
+        self.sqrt_beta_history = np.empty(history_length, dtype=np.float64)
+        self.sqrt_beta_history[0] = self.sqrt_beta
+        self.i_record = 0
+
+    def record_sample(self, half_host):                                                          # 792-795
+        if self.i_record < self.samples_history.shape[0]:
+            self.samples_history[self.i_record, :] = half_host
+            self.i_record += 1
+
+    def record_sqrt_beta(self):                                                                  # 797-799
+        if self.i_record < self.sqrt_beta_history.shape[0]:
+            self.sqrt_beta_history[self.i_record] = self.sqrt_beta
+
+
+class _DistStepper:
+    """The part of the ``pCN`` surface that ``Simulation.run`` drives (one_step, adapt_step, adapt_step_sqrtBeta, record_skip),
+    on top of a DistPCN.  ``beta`` / ``betaZ`` ARE the chain's step sizes, so the reference's adaptation rules -- borrowed
+    unchanged from mspde.image.pCN -- act on the distributed sampler directly."""
+
+    def __init__(self, chain, noise_fn, target_acceptance_rate=0.234):
+        self.chain, self.noise_fn = chain, noise_fn
+        self.aggresiveness = 0.2
+        self.target_acceptance_rate = target_acceptance_rate
+        self.beta_feedback_gain = 2.1
+        self.record_skip = 1
+        self.record_count = 0
+        self.max_record_history = 1000000
+        self.use_beta_adaptation = False            # the sqrt-beta hyper-move is not distributed (single-GPU path only)
+        self.pcn_step_sqrtBetas = 5e-1
+        self.pcn_step_sqrtBetas_Z = 0.5 ** 0.5
+        self.last_step = None
+
+    beta = property(lambda self: self.chain.beta, lambda self, v: setattr(self.chain, "beta", float(v)))
+    betaZ = property(lambda self: self.chain.betaZ, lambda self, v: setattr(self.chain, "betaZ", float(v)))
+
+    def one_step(self, Layers):
+        """pCN.one_step (553-617) through DistPCN.one_step; records the current half-samples of every layer (609-613).
+        Returns (accepted, 0); numpy.linalg.LinAlgError propagates to Simulation.run like on the single-GPU path."""
+        self.last_step = self.chain.one_step(*self.noise_fn())
+        if self.record_count % self.record_skip == 0:
+            halves = self.chain.current_halves().cpu().numpy()
+            for k, l in enumerate(Layers):
+                l.record_sample(halves[k])
+                l.record_sqrt_beta()
+        self.record_count += 1
+        return int(self.last_step["accepted"]), 0
+
+
+def _borrow_step_rules():
+    from . import image as im
+    for name in ("adapt_step", "more_aggresive", "less_aggresive", "set_step", "set_step_sqrtBeta", "adapt_step_sqrtBeta"):
+        setattr(_DistStepper, name, getattr(im.pCN, name))
+
+
+class DistSimulation:
+    """``Simulation(..., distributed=True)``: the reference's ``Simulation`` surface (image_cupy.py:810-1014: constructor
+    arguments, ``run``, ``Layers[k].samples_history``, ``acceptancePercentage``, ``total_time``) for ONE chain whose dense work
+    is block-distributed over the ranks of the default process group (BASELINE config 5).  Launch one process per GPU under
+    torchrun; every rank builds the same inputs and draws the same noise, steps the chain collectively, and holds the same
+    histories; rank 0 writes the result file.
+
+    ``run`` IS ``mspde.image.Simulation.run`` (pinned to the reference's loop by tests/test_run_loop.py); the stepper underneath
+    is DistPCN (tests/test_gpu_dist.py).  Not carried over: the sqrt-beta hyper-move and the naive Phi branch."""
+
+    def __init__(self, n_layers, n_samples, n, n_extended, beta, kappa, sigma_0, sigma_v, sigma_scaling, meas_std,
+                 evaluation_interval, printProgress, seed, burn_percentage, enable_step_adaptation, pcn_variant="dunlop",
+                 phantom_name="shepp.png", meas_type="tomo", n_theta=50, verbose=False, hybrid_GPU_CPU=False, device=0,
+                 chol_epsilon=1e-6):
+        if meas_type != "tomo" or hybrid_GPU_CPU or phantom_name != "shepp.png":
+            raise NotImplementedError("the distributed chain covers the Shepp-Logan tomography measurement on GPUs only")
+        dev = torch.device("cuda", device)
+        chain, noise_fn = build_dist_chain(n, n_extended, n_theta, n_layers, dev, seed=seed, beta=beta, meas_std=meas_std,
+                                           chol_epsilon=chol_epsilon, kappa=kappa, sigma_0=sigma_0, sigma_v=sigma_v,
+                                           sigma_scaling=sigma_scaling)
+        self._finish(chain, noise_fn, n_layers, n_samples, evaluation_interval, printProgress, burn_percentage,
+                     enable_step_adaptation, seed=seed, pcn_variant=pcn_variant, verbose=verbose)
+
+    @classmethod
+    def from_chain(cls, chain, noise_fn, n_samples, evaluation_interval=10, printProgress=False, burn_percentage=25.0,
+                   enable_step_adaptation=True, **kw):
+        """Wrap an existing DistPCN (or any object with its beta / betaZ / one_step / current_halves / sqrt_betas / nr / K)."""
+        self = object.__new__(cls)
+        self._finish(chain, noise_fn, chain.K, n_samples, evaluation_interval, printProgress, burn_percentage,
+                     enable_step_adaptation, **kw)
+        return self
+
+    def _finish(self, chain, noise_fn, n_layers, n_samples, evaluation_interval, printProgress, burn_percentage,
+                enable_step_adaptation, seed=None, pcn_variant="dunlop", verbose=False):
+        if not hasattr(_DistStepper, "adapt_step"):
+            _borrow_step_rules()
+        self.chain = chain
+        self.n_layers, self.n_samples = n_layers, n_samples
+        self.evaluation_interval, self.printProgress = evaluation_interval, printProgress
+        self.burn_percentage, self.enable_step_adaptation = burn_percentage, enable_step_adaptation
+        self.random_seed, self.pcn_variant, self.verbose = seed, pcn_variant, verbose
+        self.acceptancePercentage = 0.
+        self.accepted_count = 0
+        self.accepted_count_SqrtBeta = 0
+        self.total_time = 0.0
+        self.pcn = _DistStepper(chain, noise_fn)
+        self.pcn.record_skip = max(1, n_samples // self.pcn.max_record_history)                 # 899
+        history_length = min(n_samples, self.pcn.max_record_history)                            # 900
+        self.Layers = [_HistoryLayer(k, chain.sqrt_betas[k], history_length, chain.nr) for k in range(n_layers)]
+
+    def run(self):
+        from . import image as im
+        return im.Simulation.run(self)
+
+    def save(self, file_name):
+        """Rank 0 writes the histories and the run's scalars (key names of util._save_object where they exist, .npz)."""
+        import numpy as np
+        if dist.is_initialized() and dist.get_rank() != 0:
+            return
+        out = {"n_layers": self.n_layers, "n_samples": self.n_samples, "evaluation_interval": self.evaluation_interval,
+               "burn_percentage": self.burn_percentage, "acceptancePercentage": self.acceptancePercentage,
+               "accepted_count": self.accepted_count, "total_time": self.total_time, "pcn/beta": self.pcn.beta,
+               "pcn/betaZ": self.pcn.betaZ, "pcn/record_skip": self.pcn.record_skip}
+        for k, l in enumerate(self.Layers):
+            out[f"Layers {k}/samples_history"] = l.samples_history[:l.i_record]
+            out[f"Layers {k}/sqrt_beta"] = l.sqrt_beta
+            out[f"Layers {k}/sqrt_beta_history"] = l.sqrt_beta_history[:l.i_record]
+        np.savez(file_name, **out)

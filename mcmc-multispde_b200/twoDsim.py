@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Driver with the flag surface of /root/reference/twoDsim.py (argparse block 68-97) on top of mspde.image.
 
+``--distributed`` (not in the reference) runs ONE chain block-distributed over the ranks of a torchrun launch (n=96).
 FBP initialisation (seq-no 0) and chain continuation from the previous sequence's result file (seq-no > 0) follow
 twoDsim.py:133-136 through mspde.io.  Not carried over (out of the hot-path scope): Slurm self-resubmission and
 post_analysis plotting."""
@@ -73,6 +74,8 @@ def build_parser():
     add_boolean_argument(parser, 'verbose', default=True)
     add_boolean_argument(parser, 'hybrid', default=False)
     add_boolean_argument(parser, 'adapt-sqrtbeta', default=False)
+    # not in the reference: ONE chain block-distributed over the ranks of a torchrun launch (BASELINE config 5, mspde.dist)
+    add_boolean_argument(parser, 'distributed', default=False)
     return parser
 
 
@@ -84,8 +87,42 @@ def parse_args(argv=None):
     return args
 
 
+def run_distributed(args):
+    """--distributed under torchrun: every rank steps the same chain collectively (mspde.dist.DistSimulation); rank 0 saves."""
+    import torch
+    import torch.distributed as dist
+    from mspde.dist import DistSimulation
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.adapt_sqrtbeta or args.naive or args.seq_no != 0:
+        raise SystemExit("--distributed covers the plain pCN step from an FBP-free prior start (no --adapt-sqrtbeta, --naive, --seq-no)")
+    sim = DistSimulation(n_layers=args.n_layers, n_samples=args.n_samples, n=args.n, n_extended=args.n_extended, beta=args.beta,
+                         kappa=args.kappa, sigma_0=args.sigma_0, sigma_v=args.sigma_v, sigma_scaling=args.sigma_scaling,
+                         meas_std=args.meas_std, evaluation_interval=args.evaluation_interval,
+                         printProgress=args.print_progress and int(os.environ.get("RANK", "0")) == 0, seed=args.seed,
+                         burn_percentage=args.burn_percentage, enable_step_adaptation=args.enable_step_adaptation,
+                         pcn_variant=args.variant, phantom_name=args.phantom_name, meas_type=args.meas_type, n_theta=args.n_theta,
+                         verbose=args.verbose, hybrid_GPU_CPU=args.hybrid, device=local_rank, chol_epsilon=args.chol_epsilon)
+    sim.pcn.target_acceptance_rate = 0.234                      # twoDsim.py:107
+    sim.run()
+    parent = pathlib.Path(args.result_dir) if args.result_dir else pathlib.Path.cwd() / 'SimulationResult'
+    folder = parent / ('result-' + datetime.datetime.now().strftime('%d-%b-%Y_%H_%M_%S'))
+    if int(os.environ.get("RANK", "0")) == 0:
+        folder.mkdir(parents=True, exist_ok=True)
+        out = folder / 'result_0.npz'
+        sim.save(str(out))
+        print('simulation result stored in {} ({:.3f} it/s, acceptance {:.1%})'.format(
+            out, args.n_samples / max(sim.total_time, 1e-9), sim.acceptancePercentage))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def main(argv=None):
     args = parse_args(argv)
+    if args.distributed:
+        return run_distributed(args)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     sim = im.Simulation(n_layers=args.n_layers, n_samples=args.n_samples, n=args.n, n_extended=args.n_extended, beta=args.beta,
                         kappa=args.kappa, sigma_0=args.sigma_0, sigma_v=args.sigma_v, sigma_scaling=args.sigma_scaling,

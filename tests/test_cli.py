@@ -31,7 +31,7 @@ def test_options_parse_like_the_reference(cli, entry):
     assert set(ref) <= set(ours)
     for k, v in ref.items():
         assert ours[k] == v and type(ours[k]) is type(v), (k, ours[k], v)
-    assert set(ours) - set(ref) == {"result_dir"}                        # the one option added here
+    assert set(ours) - set(ref) == {"result_dir", "distributed"}         # the options added here
 
 
 @pytest.mark.parametrize("argv", GOLD["rejected"], ids=lambda a: " ".join(a))
@@ -44,4 +44,5 @@ def test_rejects_what_the_reference_rejects(cli, argv, capsys):
 def test_extensions(cli):
     a = cli.parse_args(["--basis-n", "96", "--result-dir", "/tmp/out", "--noenable-step-adaptation", "--noprint-progress"])
     assert a.n == 96 and a.result_dir == "/tmp/out"
-    assert a.enable_step_adaptation is False and a.print_progress is False
+    assert a.enable_step_adaptation is False and a.print_progress is False and a.distributed is False
+    assert cli.parse_args(["--distributed", "--basis-n", "96"]).distributed is True

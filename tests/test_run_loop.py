@@ -95,3 +95,71 @@ def test_step_setters_follow_the_reference_guards():
     assert pcn.pcn_step_sqrtBetas == 1.0 and pcn.pcn_step_sqrtBetas_Z == 0.0
     pcn.set_step_sqrtBeta(0.6)
     assert pcn.pcn_step_sqrtBetas_Z == pytest.approx(0.8, rel=1e-15)
+
+
+class _FakeChain:
+    """Stands in for mspde.dist.DistPCN on CPU: scripted accept flags, a state that changes when a step is accepted."""
+
+    def __init__(self, g, K=3, nr=5):
+        import torch
+        self.K, self.nr = K, nr
+        self.sqrt_betas = [3.0, 2.0, 1.0]
+        self.beta, self.betaZ = g["start"]["beta"], g["start"]["betaZ"]
+        self.fail_at = g["scenario"]["fail_at"]
+        self.calls, self.seen = 0, []
+        self.state = torch.zeros((K, nr), dtype=torch.complex128)
+
+    def one_step(self, w_half, log_u, w_last, e):
+        i = self.calls
+        self.calls += 1
+        self.seen.append([self.beta, self.betaZ])
+        if self.fail_at is not None and i == self.fail_at:
+            raise np.linalg.LinAlgError("scripted failure")
+        acc = script(i)[0]
+        if acc:
+            self.state = self.state + (i + 1)
+        return dict(accepted=bool(acc), log_ratio=0.0, phi_cur=0.0, phi_new=0.0)
+
+    def current_halves(self):
+        return self.state.clone()
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_distributed_simulation_surface_runs_the_same_loop(name, capsys):
+    """mspde.dist.DistSimulation (Simulation(..., distributed=True)): run() is Simulation.run, the step rules are pCN's, and
+    they act on the chain's own beta / betaZ.  Driven by a stand-in chain with the reference golden's accept script, the step
+    sizes the CHAIN sees at every step equal the reference's; every step's current half-samples land in the histories."""
+    from mspde import dist as md
+    g = GOLD[name]
+    sc = g["scenario"]
+    chain = _FakeChain(g)
+    sim = md.DistSimulation.from_chain(chain, lambda: (None, 0.0, None, None), sc["n_samples"], sc["evaluation_interval"],
+                                       sc["printProgress"], 25.0, sc["enable_step_adaptation"])
+    sim.pcn.target_acceptance_rate = g["start"]["target_acceptance_rate"]
+    sim.run()
+    capsys.readouterr()
+    assert chain.calls == g["calls"]
+    np.testing.assert_allclose(np.array(chain.seen), np.array(g["seen"])[:, :2], rtol=1e-14, atol=0)
+    assert chain.beta == pytest.approx(g["final"]["beta"], rel=1e-14) and chain.betaZ == pytest.approx(g["final"]["betaZ"], rel=1e-14)
+    assert sim.accepted_count == g["accepted_count"] and sim.accepted_count_SqrtBeta == 0
+    assert sim.acceptancePercentage == pytest.approx(g["acceptancePercentage"], rel=1e-15)
+    assert [l.samples_history.shape[0] for l in sim.Layers] == g["history_rows_after"]
+    if sc["fail_at"] is None:
+        # row r holds the state after step r: the sum of (i + 1) over the accepted steps i <= r
+        want = np.cumsum([(i + 1) * script(i)[0] for i in range(sc["n_samples"])])
+        for l in sim.Layers:
+            assert l.i_record == sc["n_samples"]
+            np.testing.assert_array_equal(l.samples_history[:, 0].real, want)
+            assert np.all(l.sqrt_beta_history == l.sqrt_beta)
+
+
+def test_distributed_simulation_result_file(tmp_path):
+    from mspde import dist as md
+    g = GOLD["no_adapt"]
+    sim = md.DistSimulation.from_chain(_FakeChain(g), lambda: (None, 0.0, None, None), 12, 5, False, 25.0, False)
+    sim.run()
+    path = str(tmp_path / "result_0.npz")
+    sim.save(path)
+    z = np.load(path)
+    assert int(z["n_layers"]) == 3 and z["Layers 2/samples_history"].shape == (12, 5)
+    assert float(z["pcn/beta"]) == 0.5 and int(z["accepted_count"]) == sim.accepted_count
