@@ -14,7 +14,7 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
@@ -43,7 +43,7 @@ static int g_qr_aux_prio = 0;
 extern "C" {
 
 const char* mspde_last_error(void) { return get_error(); }
-long long mspde_launch_count(void) { return g_launches; }
+long long mspde_launch_count(void) { return g_launches.load(); }
 int mspde_set_gemm_mode(int mode) { return set_gemm_mode(mode); }
 int mspde_get_gemm_mode(void) { return gemm_mode(); }
 int mspde_set_qr_block(int k) { return set_qr_block_width(k); }

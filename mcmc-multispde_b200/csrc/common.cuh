@@ -1,5 +1,6 @@
 // Shared declarations for libmspde (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -11,7 +12,7 @@ namespace mspde {
 
 void set_error(const char* fmt, ...);
 const char* get_error();
-extern long long g_launches;   // kernels launched by this library (bench.py reports it as gpu_launches)
+extern std::atomic<long long> g_launches;   // kernels launched by this library (bench.py reports it as gpu_launches)
 
 #define MSPDE_CUDA(expr)                                                                      \
     do {                                                                                      \

@@ -621,7 +621,7 @@ static int geqrf_aug_pairs(cudaStream_t st, cplx* A, int lda, int rows, int cols
     return 0;
 }
 
-static int g_qr_block = -1;    // -1: not chosen yet (environment MSPDE_QR_BLOCK = 64 | 128, default 128)
+static std::atomic<int> g_qr_block{-1};    // -1: not chosen yet (environment MSPDE_QR_BLOCK = 64 | 128, default 128)
 int qr_block_width() {
     if (g_qr_block < 0) {
         const char* e = getenv("MSPDE_QR_BLOCK");

@@ -783,8 +783,8 @@ int launch(cudaStream_t st, const GemmArgs& a, int nz) {
     return 0;
 }
 
-int g_gemm_mode = -1;   // -1: not chosen yet (environment MSPDE_GEMM = 3m | 4m, else the default)
-int g_pre_min = -1;     // -1: not chosen yet (environment MSPDE_GEMM_PRE_MIN, else 2048)
+std::atomic<int> g_gemm_mode{-1};   // -1: not chosen yet (environment MSPDE_GEMM = 3m | 4m, else the default)
+std::atomic<int> g_pre_min{-1};     // -1: not chosen yet (environment MSPDE_GEMM_PRE_MIN, else 2048)
 
 }  // namespace
 
