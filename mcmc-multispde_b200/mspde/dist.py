@@ -562,9 +562,14 @@ class DistPCN:
     (Phi(L_latest) || Gibbs QR).  The accept test runs on the host from the all-reduced Phi values, identical on every rank."""
 
     def __init__(self, n, n_ext, n_layers, H, y, D_diag, stdev_sym, sqrt_betas, device, delta=None, chol_epsilon=1e-6, beta=1.0,
-                 nb=512):
+                 nb=512, packed_gemm=False):
         from .core import MspdeContext
         self.device = device
+        if not packed_gemm:
+            # PROCESS-WIDE: large 3M products go through the in-loop kernel.  The packed-operand kernel keeps a workspace per
+            # stream (up to 6 GB each, three streams here) that the replicated N x N matrices of n=96 leave no room for, and the
+            # per-rank panel updates are short-k products it does not speed up; 5.61 s/iteration was measured this way.
+            _ffi.set_gemm_pre_min(0)
         il = 2 * n - 1
         self.n, self.n_ext, self.K = n, n_ext, n_layers
         self.N, self.nr = il * il, 2 * n * n - 2 * n + 1
