@@ -146,3 +146,26 @@ def test_value_loads_are_16_byte_aligned_and_inside_the_stage():
                     assert o % 2 == 0 and 0 <= o < stage - 1
                 for o in [x + kk * 4 * BM for x in a_sum] + [x + kk * 4 * BN for x in b_sum]:
                     assert 0 <= o < stage
+
+
+@pytest.mark.parametrize("MFi", [2, 4])
+def test_in_loop_3m_kernel_value_loads_are_conflict_free(MFi):
+    """zgemm3m_tn_kernel (struct M3): operand rows are stored with a pitch of BM + 2 / BN + 2 complex elements (== 2 mod 8), so
+    the 8 lanes of a quarter-warp (g in {2q', 2q'+1}, t = 0..3) hit 8 distinct 16-byte slots."""
+    assert "static constexpr int PA = BM + 2;" in SRC and "static constexpr int PB = BN + 2;" in SRC
+    assert "const int a_off = (t * PA + wi * 8 * MF + g) * 2;" in SRC
+    assert "const int b_off = (BK * PA + t * PB + wj * 16 + g) * 2;" in SRC
+    bm, bn, bk = 64, 32, 16
+    pa, pb = bm + 2, bn + 2
+    wi_n = bm // (8 * MFi)
+    for warp in range(wi_n * (bn // 16)):
+        wi, wj = warp % wi_n, warp // wi_n
+        for kk in range(bk // 4):
+            for q in range(4):
+                lanes = range(8 * q, 8 * q + 8)
+                for a in range(MFi):
+                    slots = {(((l & 3) * pa + wi * 8 * MFi + (l >> 2)) + kk * 4 * pa + a * 8) % 8 for l in lanes}
+                    assert len(slots) == 8
+                for b in range(2):
+                    slots = {((bk * pa + (l & 3) * pb + wj * 16 + (l >> 2)) + kk * 4 * pb + b * 8) % 8 for l in lanes}
+                    assert len(slots) == 8
