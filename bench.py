@@ -311,9 +311,10 @@ def config5_block(cfg, dev, rank, world, steps, warmup, fp64_peak, selfcheck_n=(
 
 def config5_bytes_per_rank(N, M, world):
     """Free HBM a rank needs for the n=96 distributed step: the peak seen by torch's allocator on 8 B200 was 126.5 GiB at
-    N=36481, M=17190 (profiles/r02_bench_8gpu_c.json's out-of-memory report: 106.7 GiB live + a 19.8 GiB request), which is
-    1.25 x the (M+N) x (M+N) augmented Gibbs matrix + 4 N x N + 2 M x N complex128 blocks a rank holds when world=8; scaled
-    with the same expression, plus 15 % for allocator fragmentation."""
+    N=36481, M=17190 (profiles/r02_bench_8gpu_c.json's out-of-memory report: 106.7 GiB live + a 19.8 GiB request; most of it
+    is replicated N x N matrices, so it shrinks slowly with the rank count).  Other sizes are scaled by the bytes of the
+    problem's dense matrices -- an (M+N) x (M+N) stacked matrix, four N x N, two M x N complex128: 141 GiB at n=96 -- and by
+    sqrt(8 / world); 15 % is added for allocator fragmentation (17.9 GiB were reserved-but-unallocated in that report)."""
     blocks = 16.0 * ((M + N) ** 2 + 4.0 * N * N + 2.0 * M * N)
     at8 = 16.0 * ((17190 + 36481) ** 2 + 4.0 * 36481 ** 2 + 2.0 * 17190 * 36481)
     return 1.15 * 126.5 * 2**30 * (blocks / at8) * (8.0 / world) ** 0.5
