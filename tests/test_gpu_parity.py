@@ -1040,26 +1040,3 @@ def test_multichain_runner_matches_chains_run_alone():
     assert rel(pooled[1]["u_mean"].cpu(), F.mean(0)) < 1e-11
     assert rel(pooled[1]["u_var"].cpu(), F.var(0)) < 1e-10
     sim.pcn.ctx.close()
-
-
-def test_packed_gemm_workspaces_are_returned(lib):
-    """The packed-operand kernel keeps one workspace per stream (zgemm_tn.cu: prews_get).  mspde_release_gemm_workspaces waits
-    for the device and gives all of them back; the next large product allocates afresh and produces the same bits."""
-    from mspde import _ffi
-    mode0, pre0 = _ffi.get_gemm_mode(), _ffi.get_gemm_pre_min()
-    try:
-        _ffi.set_gemm_mode(_ffi.GEMM_3M)
-        _ffi.set_gemm_pre_min(1)
-        A, B = crandn(600, 300, seed=4), crandn(600, 200, seed=5)
-        C1, C2 = crandn(300, 200, seed=6), crandn(300, 200, seed=6)
-        _gemm(lib, A, B, C1, True, 1.0, 0.0, 0)
-        freed = _ffi.release_gemm_workspaces()
-        assert freed >= (600 // 16) * 16 * (300 + 200) * 3 * 8          # at least this product's packed operands
-        assert _ffi.release_gemm_workspaces() == 0                         # nothing left to return
-        _gemm(lib, A, B, C2, True, 1.0, 0.0, 0)
-        torch.cuda.synchronize()
-        assert torch.equal(C1, C2)
-    finally:
-        _ffi.set_gemm_mode(mode0)
-        _ffi.set_gemm_pre_min(pre0)
-        _ffi.release_gemm_workspaces()
