@@ -45,6 +45,7 @@ CASES = {
     "n4k4": (4, 64, 8, 4, 0.4, 8, 3, 2, False),      # 4 layers: two middle layers
     "n8": (8, 64, 8, 3, 0.5, 9, 3, 1, False),
     "n16": (16, 64, 45, 2, 0.5, 1, 2, 0, False),     # BASELINE configs[0] geometry (2 layers, 45 angles)
+    "n4e16": (4, 16, 6, 3, 0.6, 13, 4, 2, True),     # another extended basis (31 x 31 image, M = 186): CPU pin of the oracle only
 }
 
 

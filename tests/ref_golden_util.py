@@ -16,6 +16,15 @@ from oracle import mspde_oracle as o
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+# Cases whose CUDA-path tests ran on B200s (profiles/r02_gputest_c.log).  Goldens added later pin the oracle on CPU only until
+# a GPU run has covered them; tests/test_gpu_ref_goldens.py enumerates gpu_cases().
+GPU_VERIFIED = ("n16", "n2", "n3", "n4", "n4k2", "n4k4", "n8")
+
+
+def gpu_cases(mode):
+    return [c for c in cases(mode) if c in GPU_VERIFIED]
+
+
 def cases(mode):
     return sorted(os.path.basename(p)[len("ref_step_"):-len(f"_{mode}.npz")] for p in glob.glob(os.path.join(GOLDEN, f"ref_step_*_{mode}.npz")))
 

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from ref_golden_util import RefGolden, cases, checksum_close
+from ref_golden_util import RefGolden, gpu_cases, checksum_close
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-10
@@ -59,7 +59,7 @@ def _chain_from_golden(R, ctx, beta):
     return cb
 
 
-@pytest.mark.parametrize("case", cases("alias"))
+@pytest.mark.parametrize("case", gpu_cases("alias"))
 def test_tables_bit_exact_vs_reference(case):
     """a1: FourierAnalysis_2D.__init__ tables from mspde_index_maps == the reference's own arrays, bit for bit."""
     from mspde import image as im
@@ -70,7 +70,7 @@ def test_tables_bit_exact_vs_reference(case):
     assert np.array_equal(f.D_diag, g["D_diag"])
 
 
-@pytest.mark.parametrize("case", [c for c in cases("alias") if c != "n16"])
+@pytest.mark.parametrize("case", [c for c in gpu_cases("alias") if c != "n16"])
 def test_tomography_matrix_vs_reference(case):
     """f1 / a14: H built on the device (mspde_tomography_H) and normalised as pCN.__init__ does vs the reference's own H
     (its numba kernel run under the CUDA simulator + post-fixes + /stdev), and HtH on the DMMA GEMM vs the reference's."""
@@ -87,7 +87,7 @@ def test_tomography_matrix_vs_reference(case):
         assert rel(H, g["H"]) < 1e-13
 
 
-@pytest.mark.parametrize("case", [c for c in cases("alias") if c != "n16"])
+@pytest.mark.parametrize("case", [c for c in gpu_cases("alias") if c != "n16"])
 def test_operators_vs_reference(case, gemm_mode):
     """a2-a5, a9, a11 on the reference's own inputs: coefficient tables, L, log|det L|, Phi (default and naive), lstsq."""
     R = RefGolden(case, "alias")
@@ -133,7 +133,7 @@ def test_L_bit_identical_from_reference_tables():
     ctx.close()
 
 
-@pytest.mark.parametrize("case", cases("alias"))
+@pytest.mark.parametrize("case", gpu_cases("alias"))
 def test_one_step_chain_vs_reference(case, gemm_mode):
     """a6-a12: pCN.one_step free-running over the reference's recorded steps through mspde_pcn_step."""
     if case == "n16" and gemm_mode == 0:
