@@ -283,8 +283,8 @@ def main():
     env = dict(os.environ, NUMBA_ENABLE_CUDASIM="1", NUMBA_CACHE_DIR="/tmp/nbcache")
     for case in ([args.case] if args.case else CASES):
         for mode in ([args.mode] if args.mode else ["alias", "native"]):
-            if mode == "native" and case in ("n16", "n4k4"):
-                continue
+            if mode == "native" and case in ("n16", "n4k4", "n4e16"):
+                continue        # n4e16: the reference's own complex64 QR overflows to inf/NaN at this geometry (util.lstsq, 605)
             subprocess.run([sys.executable, os.path.abspath(__file__), "--case", case, "--mode", mode], check=True, env=env)
 
 
