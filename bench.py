@@ -827,16 +827,23 @@ def main():
         torch.cuda.empty_cache()
         lost = {"unavailable": "rank 0 did not return from this block (another rank stalled or failed); the rest of the line was "
                                "measured before it started"}
-        guard = LineGuard(headline(dict(lost), dict(lost))) if rank == 0 else None
+        def arm(make_line):
+            try:
+                return LineGuard(make_line()) if rank == 0 else None
+            except Exception as ex:                     # the insurance must never cost the run
+                sys.stderr.write(f"line guard unavailable: {ex!r}\n")
+                return None
+        guard = arm(lambda: headline(dict(lost), dict(lost)))
         try:
             try:
                 config4 = config4_block(cfg, dev, rank, world, local_rank)
             except Exception as ex:                     # keep the headline line even if an extra block fails
                 config4 = {"unavailable": repr(ex)[:300]}
             if world >= 8 or args.with_config5:
-                if guard is not None:
-                    guard.disarm()
-                    guard = LineGuard(headline(config4, dict(lost)))
+                if rank == 0:
+                    if guard is not None:
+                        guard.disarm()
+                    guard = arm(lambda: headline(config4, dict(lost)))
                 try:
                     config5 = config5_block(CONFIGS[5], dev, rank, world, steps=2, warmup=1, fp64_peak=FP64_PEAK_TFLOPS,
                                             selfcheck_n=(32,), local_rank=local_rank)
